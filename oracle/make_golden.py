@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz by running the REAL reference (torchnmf 0.3.5).
+
+TEST INFRASTRUCTURE ONLY (see oracle/mu_oracle.py header).  Run in the build container, where
+the reference is importable from /root/reference (read-only) or baseline/_ref:
+
+    python oracle/make_golden.py            # small cases (seconds)
+    python oracle/make_golden.py --cfg2     # + the 200-iteration 65536x4096 R=64 KL run (~10 min CPU)
+
+The GPU box has no reference; the fixtures written here are what travels.  Inputs are generated
+from fixed torch CPU seeds: V = rand(N,C) rounded to bf16-representable values, so the
+fp32 reference and the 16-bit-operand engine consume bit-identical data; W0/H0 = |randn|.
+"""
+import argparse
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+    if os.path.isdir(os.path.join(cand, "torchnmf")):
+        sys.path.insert(0, cand)
+        break
+import torchnmf  # noqa: E402  (the reference)
+import torchnmf.nmf as ref_nmf  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def make_inputs(shape_v, shape_w, shape_h, seed_v=0, seed_f=1, floor=0.0):
+    torch.manual_seed(seed_v)
+    V = torch.rand(*shape_v).bfloat16().float()
+    if floor > 0:
+        V = V.clamp_min(floor)
+    torch.manual_seed(seed_f)
+    W0 = torch.randn(*shape_w).abs()
+    H0 = torch.randn(*shape_h).abs()
+    return V, W0, H0
+
+
+def run_reference(cls, V, W0, H0, beta, tol, max_iter, alpha, l1_ratio, trainable_W=True, trainable_H=True):
+    losses = []
+    orig = ref_nmf.beta_div
+
+    def recording(inp, tgt, b=2):
+        out = orig(inp, tgt, b)
+        losses.append(math.sqrt(2.0 * float(out)))
+        return out
+
+    ref_nmf.beta_div = recording
+    try:
+        m = cls(W=W0, H=H0, trainable_W=trainable_W, trainable_H=trainable_H)
+        n_iter = m.fit(V, beta, tol, max_iter, False, alpha, l1_ratio)
+    finally:
+        ref_nmf.beta_div = orig
+    return m.W.detach().clone(), m.H.detach().clone(), n_iter, losses
+
+
+def small_cases():
+    torch.set_num_threads(1)          # deterministic MKL reduction order for the fixtures
+    cases = {}
+    # --- NMF, ragged shape (not a multiple of any tile), all beta branches of nmf.py:61-74 ---
+    N, C, R = 97, 83, 8
+    for beta in (-1, 0, 0.5, 1, 1.5, 2, 3):
+        for alpha, l1r in ((0, 0), (0.1, 0.5)):
+            V, W0, H0 = make_inputs((N, C), (C, R), (N, R), floor=2 ** -7 if beta <= 0 else 0.0)
+            W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, beta, float("-inf"), 20, alpha, l1r)
+            cases[f"nmf_b{beta}_a{alpha}_l{l1r}"] = dict(
+                kind="nmf", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                beta=beta, tol=float("-inf"), max_iter=20, alpha=alpha, l1_ratio=l1r)
+    # --- stop rule / trainable flags ---
+    V, W0, H0 = make_inputs((N, C), (C, R), (N, R))
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 1, 1e-2, 100, 0, 0)
+    cases["nmf_stoprule"] = dict(kind="nmf", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                 beta=1, tol=1e-2, max_iter=100, alpha=0, l1_ratio=0)
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 1.5, float("-inf"), 10, 0, 0, trainable_W=False)
+    cases["nmf_frozenW"] = dict(kind="nmf", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                beta=1.5, tol=float("-inf"), max_iter=10, alpha=0, l1_ratio=0, trainable_W=False)
+    # --- BASELINE.json configs[0]: NMF 256x512 rank 16 beta=2, 50 iterations ---
+    V, W0, H0 = make_inputs((256, 512), (512, 16), (256, 16))
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 2, float("-inf"), 50, 0, 0)
+    cases["nmf_cfg1"] = dict(kind="nmf", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                             beta=2, tol=float("-inf"), max_iter=50, alpha=0, l1_ratio=0)
+    # --- tensor-core-shaped NMF case (R = 64, tile multiples and ragged edges), KL, 30 iterations ---
+    for tag, (N2, C2, R2) in (("tc", (384, 256, 64)), ("tcragged", (300, 200, 64))):
+        V, W0, H0 = make_inputs((N2, C2), (C2, R2), (N2, R2))
+        W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 1, float("-inf"), 30, 0, 0)
+        cases[f"nmf_{tag}"] = dict(kind="nmf", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                   beta=1, tol=float("-inf"), max_iter=30, alpha=0, l1_ratio=0)
+    # --- NMFD (nmf.py:776-779), batch 2, ragged sizes ---
+    B, C, L, R, T = 2, 21, 61, 4, 5
+    for beta in (0, 0.5, 1, 2, 3):
+        for alpha, l1r in ((0, 0), (0.1, 0.5)):
+            V, W0, H0 = make_inputs((B, C, L), (C, R, T), (B, R, L - T + 1), floor=2 ** -7 if beta <= 0 else 0.0)
+            W, H, n_iter, losses = run_reference(ref_nmf.NMFD, V, W0, H0, beta, float("-inf"), 20, alpha, l1r)
+            cases[f"nmfd_b{beta}_a{alpha}_l{l1r}"] = dict(
+                kind="nmfd", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                beta=beta, tol=float("-inf"), max_iter=20, alpha=alpha, l1_ratio=l1r)
+    return cases
+
+
+def save_cases(cases, fname):
+    flat = {}
+    for name, c in cases.items():
+        for k, v in c.items():
+            if isinstance(v, torch.Tensor):
+                v = v.numpy()
+            elif k == "kind":
+                v = np.array(v)
+            elif k == "losses":
+                v = np.array(v, dtype=np.float64)
+            else:
+                v = np.array(v, dtype=np.float64)
+            flat[f"{name}/{k}"] = v
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, fname), **flat)
+    print(f"wrote {fname}: {len(cases)} cases, {os.path.getsize(os.path.join(GOLD, fname)) / 1e6:.2f} MB")
+
+
+def cfg2_case(iters=200):
+    """BASELINE.json configs[1]: V (65536, 4096), R = 64, beta = 1, 200 iterations from seeds 0/1.
+    Only subsampled factor rows are stored (W rows ::8, H rows ::128); inputs are regenerated from
+    the seeds on the GPU box and verified against the float64 checksums stored here."""
+    torch.set_num_threads(os.cpu_count())
+    torch.set_flush_denormal(True)     # README.md:101-102
+    N, C, R = 65536, 4096, 64
+    V, W0, H0 = make_inputs((N, C), (C, R), (N, R))
+    t0 = time.time()
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 1, float("-inf"), iters, 0, 0)
+    dt = time.time() - t0
+    print(f"cfg2 reference: {n_iter} iterations in {dt:.1f}s ({n_iter / dt:.3f} it/s, {os.cpu_count()} threads)")
+    np.savez_compressed(
+        os.path.join(GOLD, "nmf_cfg2_kl_200.npz"),
+        W_sub=W[::8].numpy(), H_sub=H[::128].numpy(), n_iter=np.array(n_iter),
+        losses=np.array(losses, dtype=np.float64),
+        v_sum=np.array(V.double().sum().item()), w0_sum=np.array(W0.double().sum().item()),
+        h0_sum=np.array(H0.double().sum().item()),
+        w_absmax=np.array(W.abs().max().item()), h_absmax=np.array(H.abs().max().item()),
+        ref_seconds=np.array(dt), ref_threads=np.array(os.cpu_count()), iters=np.array(iters))
+    print("wrote nmf_cfg2_kl_200.npz")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg2", action="store_true")
+    ap.add_argument("--only-cfg2", action="store_true")
+    ap.add_argument("--iters", type=int, default=200)
+    a = ap.parse_args()
+    print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if not a.only_cfg2:
+        save_cases(small_cases(), "reference_small.npz")
+    if a.cfg2 or a.only_cfg2:
+        cfg2_case(a.iters)

@@ -1,0 +1,88 @@
+"""Pin the CPU oracle (oracle/mu_oracle.py) against outputs of the real reference.
+
+The fixtures in tests/golden/reference_small.npz were produced by oracle/make_golden.py, which
+imports torchnmf 0.3.5 from /root/reference and runs `fit` from identical initial factors.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mu_oracle as orc
+
+CASES = load_golden()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_fit(name):
+    c = CASES[name]
+    torch.set_num_threads(1)
+    W, H, n_iter, losses = orc.fit(
+        c["V"], c["W0"], c["H0"], beta=c["beta"], tol=c["tol"], max_iter=c["max_iter"],
+        alpha=c["alpha"], l1_ratio=c["l1_ratio"],
+        trainable_W=bool(c.get("trainable_W", 1)), trainable_H=bool(c.get("trainable_H", 1)),
+        kind=c["kind"])
+    assert n_iter == c["n_iter"]
+    # closed form vs autograd: identical maths, reduction order differs only inside BLAS calls.
+    # beta outside [1, 2] takes a gamma-th root (pow), the loosest branch.
+    rtol = 2e-5 if c["kind"] == "nmf" else 5e-5
+    assert torch.allclose(W, c["W"], rtol=rtol, atol=1e-7), (W - c["W"]).abs().max()
+    assert torch.allclose(H, c["H"], rtol=rtol, atol=1e-7), (H - c["H"]).abs().max()
+    assert len(losses) == len(c["losses"])
+    for a, b in zip(losses, c["losses"]):
+        assert math.isclose(a, b, rel_tol=1e-4, abs_tol=1e-6)
+
+
+def test_frozen_factor_is_untouched():
+    c = CASES["nmf_frozenW"]
+    assert torch.equal(c["W"], c["W0"])          # the reference itself left W alone
+    W, H, _, _ = orc.fit(c["V"], c["W0"], c["H0"], beta=c["beta"], tol=c["tol"], max_iter=c["max_iter"],
+                         trainable_W=False)
+    assert torch.equal(W, c["W0"])
+
+
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1, 1.5, 2, 3])
+def test_beta_div_nonneg_and_zero_at_equality(beta):
+    # tests/test_metrics.py:6-14 of the reference: beta_div >= 0, no NaN
+    torch.manual_seed(0)
+    x = torch.rand(50, 40) + 0.1
+    y = torch.rand(50, 40) + 0.1
+    d = orc.beta_div(x, y, beta)
+    assert not torch.isnan(d) and d >= -1e-4
+    assert abs(float(orc.beta_div(y, y, beta))) < 1e-2
+
+
+def test_beta_le0_with_zeros_raises():
+    V = torch.rand(10, 10)
+    V[0, 0] = 0
+    with pytest.raises(ValueError):
+        orc.fit(V, torch.rand(10, 3), torch.rand(10, 3), beta=0)
+
+
+def test_nmfd_reconstruct_matches_definition():
+    # nmf.py:712-713: V[i,j] ~= sum_t sum_r W[i,r,t] H[r,j-t]
+    torch.manual_seed(0)
+    W = torch.rand(5, 3, 4)
+    H = torch.rand(2, 3, 7)
+    out = orc.nmfd_reconstruct(H, W)
+    ref = torch.zeros(2, 5, 10)
+    for b in range(2):
+        for i in range(5):
+            for j in range(10):
+                for t in range(4):
+                    if 0 <= j - t < 7:
+                        ref[b, i, j] += (W[i, :, t] * H[b, :, j - t]).sum()
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_sharded_w_contractions_sum_to_full():
+    # row shards of (V, H) give partial numerators that add up (before relu/eps/l1/l2).
+    torch.manual_seed(0)
+    V = torch.rand(64, 30); W = torch.rand(30, 5); H = torch.rand(64, 5)
+    for beta in (0.5, 1, 2):
+        num, den = orc.nmf_w_contractions(V, W, H, beta)
+        n0, d0 = orc.nmf_w_contractions(V[:40], W, H[:40], beta)
+        n1, d1 = orc.nmf_w_contractions(V[40:], W, H[40:], beta)
+        assert torch.allclose(n0 + n1, num, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(d0 + d1, den, rtol=1e-5, atol=1e-6)
