@@ -1,0 +1,124 @@
+/*
+ * nmf_b200.h -- C ABI of the B200-native multiplicative-update NMF engine (libnmf_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of yoyololicon/pytorch-NMF (torchnmf 0.3.5):
+ * the body of BaseComponent.fit()'s iteration loop for dense targets
+ *
+ *     torchnmf/nmf.py:366-407   for n_iter in range(max_iter): W update, H update, loss every 10th
+ *
+ * i.e. reconstruct (nmf.py:691-693 NMF, :776-779 NMFD) + _double_backward_update (nmf.py:52-92)
+ * + the KL denominators (nmf.py:122-131) + metrics.beta_div (metrics.py:60-96).  The reference has
+ * no FFI: its seam is Python.  The binding a maintainer adds on the reference side is
+ * the ctypes stub shown in INTEGRATION.md; the Python host side shipped here
+ * (pytorch-nmf_b200/torchnmf_b200) is that stub plus the unchanged NMF/NMFD module surface.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles.  No torch / C++ types.
+ *   - all matrix pointers are DEVICE pointers to fp32, row-major, reference layout:
+ *       NMF : V (N,C)   W (C,R)   H (N,R)            V ~= H @ W^T            (nmf.py:659-662)
+ *       NMFD: V (B,C,L) W (C,R,T) H (B,R,L-T+1)      V ~= conv1d(H, flip(W)) (nmf.py:743-750)
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Every call is
+ *     asynchronous on that stream unless documented as synchronising.
+ *   - W / H are the caller's storages (the nn.Parameter .data of the reference); updates are
+ *     performed IN PLACE on them (nmf.py:92).  V is borrowed read-only.
+ *   - every function returns 0 on success; on failure a non-zero code, and
+ *     nmfb200_last_error() describes it.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef NMF_B200_H_
+#define NMF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMFB200_ABI_VERSION 1
+
+/* arithmetic mode of the contraction kernels */
+enum {
+  NMFB200_PREC_AUTO      = -1, /* f16 split tensor-core path when shape/beta allow it, else f32   */
+  NMFB200_PREC_F32       = 0,  /* fused CUDA-core kernels, fp32 operands and accumulators (exact) */
+  NMFB200_PREC_F16       = 1,  /* tcgen05, fp16 operands, fp32 accumulate                         */
+  NMFB200_PREC_F16_SPLIT = 2   /* tcgen05, fp16 hi/lo split factors (~22-bit), fp16 ratio tile    */
+};
+
+/* error codes */
+enum {
+  NMFB200_OK = 0,
+  NMFB200_ERR_INVALID = 1,     /* bad argument / unsupported shape for the requested mode */
+  NMFB200_ERR_CUDA = 2,        /* CUDA runtime / driver error                             */
+  NMFB200_ERR_STATE = 3        /* call order violated (e.g. update before set_target)     */
+};
+
+typedef struct nmfb200_ctx nmfb200_ctx;
+
+int         nmfb200_abi_version(void);
+const char* nmfb200_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t     nmfb200_launch_count(void);
+
+/* ---- dense NMF ------------------------------------------------------------------------- */
+
+/* Allocate the engine workspace for an (N,C) target of rank R on CUDA device `device`.
+ * Mirrors the sizes fixed by NMF.__init__ (nmf.py:679-689). */
+int nmfb200_nmf_create(nmfb200_ctx** out, int device, int64_t N, int64_t C, int64_t R, int precision);
+void nmfb200_destroy(nmfb200_ctx* ctx);
+/* which NMFB200_PREC_* the context resolved to */
+int nmfb200_precision(const nmfb200_ctx* ctx);
+
+/* Register the target V (device fp32, leading dimension ldv >= C).  Builds the engine-private
+ * operand copies and the V-only loss terms.  Replaces nothing in the reference: V is simply the
+ * argument of fit() (nmf.py:299).  Asynchronous. */
+int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* stream);
+/* min / max of the registered target (fit()'s validation, nmf.py:329-336).  Synchronises. */
+int nmfb200_target_minmax(nmfb200_ctx* ctx, float* vmin, float* vmax, void* stream);
+
+/* Tell the engine the fp32 factors changed outside its own update calls (fit() entry,
+ * load_state_dict, a frozen factor): rebuilds operand copies and column sums.  Asynchronous. */
+int nmfb200_nmf_sync_factors(nmfb200_ctx* ctx, const float* W, const float* H, void* stream);
+
+/* One W update, nmf.py:367-378:  W <- W * ((relu(Pn^T H)+eps) / den)^gamma  in place.
+ * l1_reg / l2_reg as computed at nmf.py:348-349; gamma as nmf.py:341-346. */
+int nmfb200_nmf_update_w(nmfb200_ctx* ctx, float* W, const float* H,
+                         double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+/* One H update with the current (already updated) W, nmf.py:380-391. */
+int nmfb200_nmf_update_h(nmfb200_ctx* ctx, const float* W, float* H,
+                         double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+/* beta_div(H W^T, V, beta) (metrics.py:60-96) accumulated into the DEVICE double *loss_dev
+ * (one element, overwritten).  Row shards add: the sum over ranks is the global divergence. */
+int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
+                     double* loss_dev, void* stream);
+
+/* Row-sharded W update.  `partial` is a device fp32 buffer of
+ * nmfb200_nmf_w_partial_numel() elements receiving this shard's raw numerator (C*R), then either
+ * colsum(H_local) (R, beta == 1) or the raw denominator (C*R).  The caller sum-all-reduces it and
+ * passes the reduced buffer to _w_apply, which performs nmf.py:78-92 on every rank identically. */
+int64_t nmfb200_nmf_w_partial_numel(const nmfb200_ctx* ctx, double beta);
+int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
+                          float* partial, void* stream);
+int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced,
+                        double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+
+/* Profiling aid for bench.py's roofline line: launches ONLY the fused contraction kernel of the W update
+ * (which = 0) or the H update (which = 1) into the engine's scratch, leaving W and H untouched. */
+int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta,
+                              void* stream);
+
+/* ---- NMFD (1-D convolutive NMF) ---------------------------------------------------------- */
+
+/* Sizes as NMFD.__init__ (nmf.py:762-774): V (B,C,L), W (C,R,T), H (B,R,L-T+1). */
+int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int64_t L,
+                        int64_t R, int64_t T, int precision);
+int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream);
+int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H,
+                          double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H,
+                          double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
+                      double* loss_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMF_B200_H_ */

@@ -1,0 +1,411 @@
+// C ABI of libnmf_b200 (see include/nmf_b200.h): context management and the per-update call graphs.
+#include "../../include/nmf_b200.h"
+
+#include <atomic>
+#include <new>
+
+#include "common.cuh"
+#include "tc_nmf.cuh"
+
+namespace nmfb200 {
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace nmfb200
+
+using namespace nmfb200;
+
+struct nmfb200_ctx {
+  int kind = 0;            // 0 = NMF, 1 = NMFD
+  int device = 0;
+  int precision = NMFB200_PREC_F32;
+  int64_t N = 0, C = 0, R = 0;
+  NmfdShape d{};
+  const float* V = nullptr;
+  int64_t ldv = 0;
+  bool has_target = false;
+  // chunked partial numerators / denominators of the CUDA-core path
+  float* num = nullptr;
+  float* den = nullptr;
+  int64_t part_floats = 0;
+  int nch_w = 1, nch_h = 1;
+  float* colsum = nullptr;        // [2][R]: 0 = colsum(W), 1 = colsum(H)
+  float* cs_scratch = nullptr;
+  int64_t cs_scratch_floats = 0;
+  double* loss_blocks = nullptr;
+  int loss_max_blocks = 0;
+  float* mm_scratch = nullptr;    // 2048 + 2
+  // NMFD
+  float* Pn = nullptr;
+  float* Pp = nullptr;
+  int dgrad_nsplit = 1;
+  // tensor-core path state (tc_nmf.cu)
+  TcState* tc = nullptr;
+};
+
+namespace {
+
+int fail(int code, const std::string& msg) { set_error(msg); return code; }
+
+#define CTX_GUARD(ctx, want_kind)                                                   \
+  if (!(ctx)) return fail(NMFB200_ERR_INVALID, "null context");                     \
+  if ((ctx)->kind != (want_kind)) return fail(NMFB200_ERR_INVALID, "wrong context kind"); \
+  NMF_CUDA_CHECK(cudaSetDevice((ctx)->device));
+
+int chunks_for(int64_t rows, int64_t cols) {
+  int64_t rb = ceil_div(rows, 64), tiles = ceil_div(cols, 64);
+  int64_t want = ceil_div(148 * 4, rb);
+  if (want > tiles) want = tiles;
+  if (want > 32) want = 32;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int ensure_den(nmfb200_ctx* c) {
+  if (!c->den) NMF_CUDA_CHECK(cudaMalloc(&c->den, c->part_floats * sizeof(float)));
+  return 0;
+}
+
+void free_ctx(nmfb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->tc) tc_destroy(c->tc);
+  cudaFree(c->num); cudaFree(c->den); cudaFree(c->colsum); cudaFree(c->cs_scratch);
+  cudaFree(c->loss_blocks); cudaFree(c->mm_scratch); cudaFree(c->Pn); cudaFree(c->Pp);
+  delete c;
+}
+
+// CUDA-core contraction of one NMF factor update into c->num / c->den (chunked partials).
+int simt_contract_w(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
+  // F = W (C rows), G = H (N rows), Vm = V^T
+  if (beta != 1.0) { int e = ensure_den(c); if (e) return e; }
+  return simt_nmf_contract(c->V, c->ldv, /*trans=*/1, W, H, c->C, c->N, (int)c->R, beta, c->nch_w, c->num,
+                           c->den, c->R, c->C * c->R, st);
+}
+int simt_contract_h(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
+  if (beta != 1.0) { int e = ensure_den(c); if (e) return e; }
+  return simt_nmf_contract(c->V, c->ldv, /*trans=*/0, H, W, c->N, c->C, (int)c->R, beta, c->nch_h, c->num,
+                           c->den, c->R, c->N * c->R, st);
+}
+
+bool use_tc(const nmfb200_ctx* c, double beta) { return c->tc != nullptr && tc_supports_beta(c->tc, beta); }
+
+}  // namespace
+
+extern "C" {
+
+int nmfb200_abi_version(void) { return NMFB200_ABI_VERSION; }
+const char* nmfb200_last_error(void) { return g_err.c_str(); }
+int64_t nmfb200_launch_count(void) { return g_launches.load(); }
+
+int nmfb200_nmf_create(nmfb200_ctx** out, int device, int64_t N, int64_t C, int64_t R, int precision) {
+  if (!out) return fail(NMFB200_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (N < 1 || C < 1 || R < 1) return fail(NMFB200_ERR_INVALID, "N, C, R must be positive");
+  if (R > 256) return fail(NMFB200_ERR_INVALID, "rank > 256 is not supported");
+  if (precision < NMFB200_PREC_AUTO || precision > NMFB200_PREC_F16_SPLIT)
+    return fail(NMFB200_ERR_INVALID, "unknown precision mode");
+  NMF_CUDA_CHECK(cudaSetDevice(device));
+  nmfb200_ctx* c = new (std::nothrow) nmfb200_ctx();
+  if (!c) return fail(NMFB200_ERR_INVALID, "out of host memory");
+  c->kind = 0; c->device = device; c->N = N; c->C = C; c->R = R;
+  int resolved = precision;
+  if (precision == NMFB200_PREC_AUTO) resolved = tc_shape_supported(N, C, R) ? NMFB200_PREC_F16_SPLIT : NMFB200_PREC_F32;
+  if (resolved != NMFB200_PREC_F32 && !tc_shape_supported(N, C, R)) {
+    delete c;
+    return fail(NMFB200_ERR_INVALID, "shape not supported by the tensor-core path (need R <= 128)");
+  }
+  c->precision = resolved;
+  c->nch_w = chunks_for(C, N);
+  c->nch_h = chunks_for(N, C);
+  int64_t pf = (int64_t)c->nch_w * C * R;
+  if ((int64_t)c->nch_h * N * R > pf) pf = (int64_t)c->nch_h * N * R;
+  c->part_floats = pf;
+  int64_t csf = colsum_scratch_floats(N > C ? N : C, (int)R, 1);
+  c->cs_scratch_floats = csf;
+  c->loss_max_blocks = simt_nmf_max_blocks(N, C);
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&c->num, pf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->colsum, 2 * R * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->cs_scratch, csf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->loss_blocks, (size_t)c->loss_max_blocks * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->mm_scratch, 2050 * sizeof(float));
+  if (e != cudaSuccess) {
+    free_ctx(c);
+    return fail(NMFB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  if (resolved != NMFB200_PREC_F32) {
+    int rc = tc_create(&c->tc, device, N, C, R, resolved == NMFB200_PREC_F16_SPLIT);
+    if (rc) { free_ctx(c); return rc; }
+  }
+  *out = c;
+  return 0;
+}
+
+void nmfb200_destroy(nmfb200_ctx* ctx) { free_ctx(ctx); }
+
+int nmfb200_precision(const nmfb200_ctx* ctx) { return ctx ? ctx->precision : -100; }
+
+int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!V || ldv < ctx->C) return fail(NMFB200_ERR_INVALID, "bad target pointer / leading dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->V = V; ctx->ldv = ldv; ctx->has_target = true;
+  int rc = matrix_minmax(V, ctx->N, ctx->C, ldv, ctx->mm_scratch, ctx->mm_scratch + 2048, st);
+  if (rc) return rc;
+  if (ctx->tc) return tc_set_target(ctx->tc, V, ldv, ctx->mm_scratch + 2048, st);
+  return 0;
+}
+
+int nmfb200_target_minmax(nmfb200_ctx* ctx, float* vmin, float* vmax, void* stream) {
+  if (!ctx) return fail(NMFB200_ERR_INVALID, "null context");
+  NMF_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  float mm[2];
+  NMF_CUDA_CHECK(cudaMemcpyAsync(mm, ctx->mm_scratch + 2048, sizeof(mm), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  NMF_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (vmin) *vmin = mm[0];
+  if (vmax) *vmax = mm[1];
+  return 0;
+}
+
+int nmfb200_nmf_sync_factors(nmfb200_ctx* ctx, const float* W, const float* H, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  if (ctx->tc) tc_mark_dirty(ctx->tc, true, true);
+  return 0;   // operand copies are rebuilt lazily; the CUDA-core path reads the fp32 factors directly
+}
+
+int nmfb200_nmf_update_w(nmfb200_ctx* ctx, float* W, const float* H, double beta, double gamma, double l1_reg,
+                         double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta)) return tc_update_w(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, st);
+  int rc = simt_contract_w(ctx, W, H, beta, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {
+    kl = ctx->colsum + ctx->R;
+    rc = factor_colsum(H, ctx->N, (int)ctx->R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);
+    if (rc) return rc;
+  }
+  ApplyArgs a{};
+  a.param = W; a.numel = ctx->C * ctx->R; a.R = (int)ctx->R; a.inner = 1; a.rowlen = ctx->R;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->nch_w;
+  a.chunk_stride = ctx->C * ctx->R; a.ldp = ctx->R; a.kl_den = kl; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  rc = apply_update(a, st);
+  if (rc) return rc;
+  if (ctx->tc) tc_mark_dirty(ctx->tc, true, false);
+  return 0;
+}
+
+int nmfb200_nmf_update_h(nmfb200_ctx* ctx, const float* W, float* H, double beta, double gamma, double l1_reg,
+                         double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta)) return tc_update_h(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, st);
+  int rc = simt_contract_h(ctx, W, H, beta, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {
+    kl = ctx->colsum;
+    rc = factor_colsum(W, ctx->C, (int)ctx->R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);
+    if (rc) return rc;
+  }
+  ApplyArgs a{};
+  a.param = H; a.numel = ctx->N * ctx->R; a.R = (int)ctx->R; a.inner = 1; a.rowlen = ctx->R;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->nch_h;
+  a.chunk_stride = ctx->N * ctx->R; a.ldp = ctx->R; a.kl_den = kl; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  rc = apply_update(a, st);
+  if (rc) return rc;
+  if (ctx->tc) tc_mark_dirty(ctx->tc, false, true);
+  return 0;
+}
+
+int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta, double* loss_dev,
+                     void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !loss_dev) return fail(NMFB200_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta) && tc_supports_loss(ctx->tc, beta)) return tc_loss(ctx->tc, W, H, beta, loss_dev, st);
+  return simt_nmf_loss(ctx->V, ctx->ldv, H, W, ctx->N, ctx->C, (int)ctx->R, beta, ctx->loss_blocks,
+                       ctx->loss_max_blocks, loss_dev, st);
+}
+
+int64_t nmfb200_nmf_w_partial_numel(const nmfb200_ctx* ctx, double beta) {
+  if (!ctx || ctx->kind != 0) return -1;
+  return beta == 1.0 ? ctx->C * ctx->R + ctx->R : 2 * ctx->C * ctx->R;
+}
+
+int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, double beta, float* partial,
+                          void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !partial) return fail(NMFB200_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta)) return tc_w_partial(ctx->tc, W, H, beta, partial, st);
+  int rc = simt_contract_w(ctx, W, H, beta, st);
+  if (rc) return rc;
+  const int64_t CR = ctx->C * ctx->R;
+  rc = reduce_chunks(ctx->num, ctx->nch_w, CR, ctx->C, (int)ctx->R, ctx->R, partial, st);
+  if (rc) return rc;
+  if (beta == 1.0)
+    return factor_colsum(H, ctx->N, (int)ctx->R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, partial + CR, st);
+  return reduce_chunks(ctx->den, ctx->nch_w, CR, ctx->C, (int)ctx->R, ctx->R, partial + CR, st);
+}
+
+int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced, double beta, double gamma,
+                        double l1_reg, double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!W || !reduced) return fail(NMFB200_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t CR = ctx->C * ctx->R;
+  ApplyArgs a{};
+  a.param = W; a.numel = CR; a.R = (int)ctx->R; a.inner = 1; a.rowlen = ctx->R;
+  a.num = reduced; a.den = beta == 1.0 ? nullptr : reduced + CR; a.nchunks = 1; a.chunk_stride = 0;
+  a.ldp = ctx->R; a.kl_den = beta == 1.0 ? reduced + CR : nullptr; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  int rc = apply_update(a, st);
+  if (rc) return rc;
+  if (ctx->tc) tc_mark_dirty(ctx->tc, true, false);
+  return 0;
+}
+
+int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta,
+                              void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta)) return tc_contract_only(ctx->tc, W, H, which, beta, st);
+  return which == 0 ? simt_contract_w(ctx, W, H, beta, st) : simt_contract_h(ctx, W, H, beta, st);
+}
+
+/* ---- NMFD ------------------------------------------------------------------------------------ */
+
+int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int64_t L, int64_t R, int64_t T,
+                        int precision) {
+  if (!out) return fail(NMFB200_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (B < 1 || C < 1 || R < 1 || T < 1 || L < T) return fail(NMFB200_ERR_INVALID, "bad NMFD sizes");
+  if (R > 256) return fail(NMFB200_ERR_INVALID, "rank > 256 is not supported");
+  if (precision != NMFB200_PREC_AUTO && precision != NMFB200_PREC_F32)
+    return fail(NMFB200_ERR_INVALID, "NMFD currently runs in fp32 only");
+  if (B * C * L > (int64_t)1 << 40) return fail(NMFB200_ERR_INVALID, "NMFD target too large");
+  NMF_CUDA_CHECK(cudaSetDevice(device));
+  nmfb200_ctx* c = new (std::nothrow) nmfb200_ctx();
+  if (!c) return fail(NMFB200_ERR_INVALID, "out of host memory");
+  c->kind = 1; c->device = device; c->precision = NMFB200_PREC_F32; c->R = R;
+  c->d = NmfdShape{(int)B, (int)C, (int)L, (int)R, (int)T, (int)(L - T + 1)};
+  c->dgrad_nsplit = nmfd_dgrad_nsplit(c->d);
+  int64_t pf = C * R * T;
+  int64_t hf = (int64_t)c->dgrad_nsplit * B * R * c->d.Lin;
+  if (hf > pf) pf = hf;
+  c->part_floats = pf;
+  int64_t cs1 = colsum_scratch_floats(C, (int)R, T), cs2 = colsum_scratch_floats(B, (int)R, c->d.Lin);
+  c->cs_scratch_floats = cs1 > cs2 ? cs1 : cs2;
+  c->loss_max_blocks = nmfd_max_blocks(c->d);
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&c->num, pf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->colsum, 2 * R * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->cs_scratch, c->cs_scratch_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->loss_blocks, (size_t)c->loss_max_blocks * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->mm_scratch, 2050 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->Pn, (size_t)B * C * L * sizeof(float));
+  if (e != cudaSuccess) {
+    free_ctx(c);
+    return fail(NMFB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return 0;
+}
+
+int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream) {
+  CTX_GUARD(ctx, 1);
+  if (!V) return fail(NMFB200_ERR_INVALID, "null target");
+  ctx->V = V; ctx->has_target = true;
+  return matrix_minmax(V, (int64_t)ctx->d.B * ctx->d.C, ctx->d.L, ctx->d.L, ctx->mm_scratch,
+                       ctx->mm_scratch + 2048, (cudaStream_t)stream);
+}
+
+static int nmfd_phi(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
+  if (beta != 1.0) {
+    if (!c->Pp) NMF_CUDA_CHECK(cudaMalloc(&c->Pp, (size_t)c->d.B * c->d.C * c->d.L * sizeof(float)));
+    int e = ensure_den(c);
+    if (e) return e;
+  }
+  return nmfd_recon_phi(c->d, c->V, W, H, beta, c->Pn, c->Pp, nullptr, 0, nullptr, st);
+}
+
+int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double beta, double gamma, double l1_reg,
+                          double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 1);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NmfdShape& d = ctx->d;
+  int rc = nmfd_phi(ctx, W, H, beta, st);
+  if (rc) return rc;
+  rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {
+    kl = ctx->colsum + d.R;
+    rc = factor_colsum(H, d.B, d.R, d.Lin, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);   // nmf.py:122-125
+  } else {
+    rc = nmfd_wgrad(d, ctx->Pp, H, ctx->den, st);
+  }
+  if (rc) return rc;
+  ApplyArgs a{};
+  a.param = W; a.numel = (int64_t)d.C * d.R * d.T; a.R = d.R; a.inner = d.T; a.rowlen = (int64_t)d.R * d.T;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = 1; a.chunk_stride = 0;
+  a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  return apply_update(a, st);
+}
+
+int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double beta, double gamma, double l1_reg,
+                          double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 1);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NmfdShape& d = ctx->d;
+  int rc = nmfd_phi(ctx, W, H, beta, st);
+  if (rc) return rc;
+  rc = nmfd_dgrad(d, ctx->Pn, W, ctx->num, ctx->dgrad_nsplit, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {
+    kl = ctx->colsum;
+    rc = factor_colsum(W, d.C, d.R, d.T, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);     // nmf.py:128-131
+  } else {
+    rc = nmfd_dgrad(d, ctx->Pp, W, ctx->den, ctx->dgrad_nsplit, st);
+  }
+  if (rc) return rc;
+  ApplyArgs a{};
+  a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->dgrad_nsplit;
+  a.chunk_stride = a.numel; a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  return apply_update(a, st);
+}
+
+int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta, double* loss_dev,
+                      void* stream) {
+  CTX_GUARD(ctx, 1);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !loss_dev) return fail(NMFB200_ERR_INVALID, "null pointer");
+  return nmfd_recon_phi(ctx->d, ctx->V, W, H, beta, nullptr, nullptr, ctx->loss_blocks, ctx->loss_max_blocks,
+                        loss_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Shared declarations for the libnmf_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace nmfb200 {
+
+// torchnmf/constants.py:3 -- float32 machine epsilon, 2^-23
+constexpr float kEps = 1.1920928955078125e-07f;
+
+// beta-divergence branch of nmf.py:61-74 / metrics.py:60-96
+enum BetaMode : int { kKL = 0, kEU = 1, kIS = 2, kGeneric = 3 };
+inline BetaMode beta_mode(double beta) {
+  if (beta == 1.0) return kKL;
+  if (beta == 2.0) return kEU;
+  if (beta == 0.0) return kIS;
+  return kGeneric;
+}
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define NMF_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      nmfb200::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+      return 2;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+#define NMF_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    nmfb200::count_launch();                                                              \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      nmfb200::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));        \
+      return 2;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ------------------------------------------------------------------------------------------
+// Launch wrappers implemented in the .cu files (all asynchronous on `st`, return 0 / error code)
+// ------------------------------------------------------------------------------------------
+
+// simt_nmf.cu ------------------------------------------------------------------------------
+// Partial contractions of one factor update on CUDA cores, fp32:
+//   S = F G^T (Mr x Nc),  (Pn, Pp) = phi_beta(Vm, S)          [nmf.py:61-74]
+//   num[ch][m][r] = sum_{c in chunk ch} Pn[m,c] G[c,r]          [nmf.py:77]
+//   den[ch][m][r] = sum_{c in chunk ch} Pp[m,c] G[c,r]          [nmf.py:82, beta != 1 only]
+// Vm[m,c] = V[m*ldv + c] (trans = 0) or V[c*ldv + m] (trans = 1).
+int simt_nmf_contract(const float* V, int64_t ldv, int trans, const float* F, const float* G,
+                      int64_t Mr, int64_t Nc, int R, double beta, int nchunks,
+                      float* num, float* den, int64_t ldp, int64_t chunk_stride, cudaStream_t st);
+// beta_div(F G^T, Vm) accumulated into block partials then *loss_dev (double).  v_const is unused here.
+int simt_nmf_loss(const float* V, int64_t ldv, const float* F, const float* G, int64_t Mr, int64_t Nc,
+                  int R, double beta, double* block_partials, int max_blocks, double* loss_dev,
+                  cudaStream_t st);
+int simt_nmf_max_blocks(int64_t Mr, int64_t Nc);
+
+// update.cu --------------------------------------------------------------------------------
+// nmf.py:78-92 on a flattened parameter of `numel` elements whose rank index is
+// r = (idx / inner) % R.   num/den are sums over `nchunks` partial slabs (stride chunk_stride,
+// row pitch ldp for a (rows x R*inner) view: element idx -> (idx / rowlen) * ldp + idx % rowlen).
+struct ApplyArgs {
+  float* param; int64_t numel; int R; int64_t inner; int64_t rowlen;
+  const float* num; const float* den; int nchunks; int64_t chunk_stride; int64_t ldp;
+  const float* kl_den;     // [R] when beta == 1 (den == nullptr)
+  const float* out_scale;  // device scalar multiplying num/den partials (nullptr = 1)
+  float gamma, l1, l2;
+  unsigned int* absmax_bits;  // optional: atomicMax of the updated values (non-negative floats)
+};
+int apply_update(const ApplyArgs& a, cudaStream_t st);
+// sums[r] = sum over all other dims of x viewed as (outer, R, inner); deterministic two-stage.
+int factor_colsum(const float* x, int64_t outer, int R, int64_t inner, float* scratch, int64_t scratch_floats,
+                  float* sums, cudaStream_t st);
+int64_t colsum_scratch_floats(int64_t outer, int R, int64_t inner);
+// dst[i] = sum_ch src[ch*stride + i]   (chunk reduction for the sharded partial buffers)
+int reduce_chunks(const float* src, int nchunks, int64_t chunk_stride, int64_t rows, int R, int64_t ldp,
+                  float* dst, cudaStream_t st);
+// min / max of a strided fp32 matrix (fit()'s validation), results in mm[0..1]
+int matrix_minmax(const float* V, int64_t rows, int64_t cols, int64_t ld, float* scratch2048, float* mm,
+                  cudaStream_t st);
+// *out = sum of n doubles in fixed order (single block)
+int sum_partials(const double* p, int n, double* out, cudaStream_t st);
+
+// nmfd.cu ----------------------------------------------------------------------------------
+struct NmfdShape { int B, C, L, R, T, Lin; };
+// WH = conv(H, W); writes Pn (and Pp when beta != 1) (B,C,L) or, when loss_blocks != nullptr,
+// reduces beta_div(WH, V) instead.
+int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const float* H, double beta,
+                   float* Pn, float* Pp, double* loss_blocks, int max_blocks, double* loss_dev,
+                   cudaStream_t st);
+int nmfd_max_blocks(const NmfdShape& s);
+// out[c,r,t] = sum_{b,l} G[b,c,l] H[b,r,l-t]
+int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, cudaStream_t st);
+// out[split][b,r,j] = sum_{c in split, t} W[c,r,t] G[b,c,j+t]
+int nmfd_dgrad(const NmfdShape& s, const float* G, const float* W, float* out, int nsplit, cudaStream_t st);
+int nmfd_dgrad_nsplit(const NmfdShape& s);
+
+}  // namespace nmfb200

@@ -1,0 +1,27 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path of the dense NMF update -- interface used by capi.cu.
+#pragma once
+#include "common.cuh"
+
+namespace nmfb200 {
+
+struct TcState;
+
+// shapes the tcgen05 kernels accept (rank padded to 64 or 128 columns)
+bool tc_shape_supported(int64_t N, int64_t C, int64_t R);
+int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool split);
+void tc_destroy(TcState* s);
+bool tc_supports_beta(const TcState* s, double beta);
+bool tc_supports_loss(const TcState* s, double beta);
+// minmax_dev: device float[2] = {min(V), max(V)} already queued on `st`
+int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st);
+// the fp32 factor changed outside the tensor-core path: operand copies must be rebuilt before use
+void tc_mark_dirty(TcState* s, bool w, bool h);
+int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,
+                cudaStream_t st);
+int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
+                cudaStream_t st);
+int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st);
+int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st);
+int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st);
+
+}  // namespace nmfb200

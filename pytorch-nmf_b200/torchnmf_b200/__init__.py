@@ -1,0 +1,6 @@
+"""torchnmf_b200 -- B200-native (sm_100a) multiplicative-update NMF engine behind the
+torchnmf.nmf.NMF / NMFD module surface.  See DESIGN.md / INTEGRATION.md at the repo root."""
+__version__ = "0.1.0"
+
+from . import constants, nmf  # noqa: F401
+from .nmf import NMF, NMFD, BaseComponent  # noqa: F401

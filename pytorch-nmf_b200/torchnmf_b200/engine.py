@@ -1,0 +1,212 @@
+"""Host-side engines: thin owners of an ``nmfb200_ctx`` plus the row-sharded W update.
+
+An engine exposes exactly the operations ``BaseComponent.fit`` (nmf.py:366-407 in the reference)
+needs from its loop body:
+
+    minmax() -> (vmin, vmax)       fit()'s validation, nmf.py:329-336
+    update_w / update_h            nmf.py:367-391
+    loss(beta) -> float            metrics.beta_div of the current reconstruction, nmf.py:360-361,:400-401
+
+`ShardedEngine` wraps any engine that also offers ``w_partial`` / ``w_apply`` / ``loss_tensor`` and
+inserts the one collective per iteration that the row-sharded layout needs.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_f32_cuda(t, name, device):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype}); the engine mirrors the reference's default dtype")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+class _CudaEngine:
+    kind = None
+
+    def __init__(self):
+        self._lib = _capi.load()
+        self._ctx = ctypes.c_void_p()
+        self._loss = None
+
+    def close(self):
+        if self._ctx:
+            self._lib.nmfb200_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def precision(self):
+        return _capi.PRECISION_NAMES[self._lib.nmfb200_precision(self._ctx)]
+
+    def minmax(self):
+        vmin, vmax = ctypes.c_float(), ctypes.c_float()
+        _capi.check(self._lib.nmfb200_target_minmax(self._ctx, ctypes.byref(vmin), ctypes.byref(vmax),
+                                                    _stream(self.device)))
+        return vmin.value, vmax.value
+
+    def loss(self, beta):
+        return float(self.loss_tensor(beta).item())
+
+
+class CudaNmfEngine(_CudaEngine):
+    """Dense NMF on one GPU: V (N,C), W (C,R), H (N,R), all fp32 CUDA tensors (W, H updated in place)."""
+    kind = "nmf"
+
+    def __init__(self, V, W, H, precision="auto"):
+        super().__init__()
+        self.device = W.device
+        for t, n in ((V, "V"), (W, "W"), (H, "H")):
+            _check_f32_cuda(t, n, self.device)
+        N, C = V.shape
+        R = W.shape[1]
+        assert W.shape == (C, R) and H.shape == (N, R)
+        self.V, self.W, self.H = V, W, H
+        self.N, self.C, self.R = N, C, R
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _capi.check(self._lib.nmfb200_nmf_create(ctypes.byref(self._ctx), dev_index, N, C, R,
+                                                 _capi.PRECISIONS[precision]))
+        self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.nmfb200_nmf_set_target(self._ctx, _ptr(V), V.stride(0), _stream(self.device)))
+        self.sync()
+
+    def sync(self):
+        _capi.check(self._lib.nmfb200_nmf_sync_factors(self._ctx, _ptr(self.W), _ptr(self.H), _stream(self.device)))
+
+    def update_w(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_update_w(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                   l2_reg, _stream(self.device)))
+
+    def update_h(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_update_h(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                   l2_reg, _stream(self.device)))
+
+    def loss_tensor(self, beta):
+        _capi.check(self._lib.nmfb200_nmf_loss(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
+                                               _stream(self.device)))
+        return self._loss
+
+    def contract_only(self, which, beta):
+        """bench.py: launch only the fused contraction kernel (0 = W update's, 1 = H update's)."""
+        _capi.check(self._lib.nmfb200_nmf_contract_only(self._ctx, _ptr(self.W), _ptr(self.H), which, beta,
+                                                        _stream(self.device)))
+
+    # --- pieces of the row-sharded W update -------------------------------------------------
+    def w_partial(self, beta):
+        n = int(self._lib.nmfb200_nmf_w_partial_numel(self._ctx, beta))
+        buf = torch.empty(n, dtype=torch.float32, device=self.device)
+        _capi.check(self._lib.nmfb200_nmf_w_partial(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(buf),
+                                                    _stream(self.device)))
+        return buf
+
+    def w_apply(self, reduced, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_w_apply(self._ctx, _ptr(self.W), _ptr(reduced), beta, gamma, l1_reg,
+                                                  l2_reg, _stream(self.device)))
+
+
+class CudaNmfdEngine(_CudaEngine):
+    """NMFD on one GPU: V (B,C,L), W (C,R,T), H (B,R,L-T+1)."""
+    kind = "nmfd"
+
+    def __init__(self, V, W, H, precision="auto"):
+        super().__init__()
+        self.device = W.device
+        for t, n in ((V, "V"), (W, "W"), (H, "H")):
+            _check_f32_cuda(t, n, self.device)
+        B, C, L = V.shape
+        _, R, T = W.shape
+        assert W.shape == (C, R, T) and H.shape == (B, R, L - T + 1)
+        self.V, self.W, self.H = V, W, H
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _capi.check(self._lib.nmfb200_nmfd_create(ctypes.byref(self._ctx), dev_index, B, C, L, R, T,
+                                                  _capi.PRECISIONS[precision]))
+        self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.nmfb200_nmfd_set_target(self._ctx, _ptr(V), _stream(self.device)))
+
+    def sync(self):
+        pass
+
+    def update_w(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmfd_update_w(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                    l2_reg, _stream(self.device)))
+
+    def update_h(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmfd_update_h(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                    l2_reg, _stream(self.device)))
+
+    def loss_tensor(self, beta):
+        _capi.check(self._lib.nmfb200_nmfd_loss(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
+                                                _stream(self.device)))
+        return self._loss
+
+
+class ShardedEngine:
+    """Row-sharded NMF over a process group: every rank holds V[n_g,:], H[n_g,:] and a replica of W.
+
+    H update and phi stage are local.  The W update is `local raw contraction -> ONE sum-all-reduce ->
+    identical ratio stage on every rank` (relu/eps/l1/l2/gamma are applied after the reduction because
+    they are not linear).  The loss is one more scalar all-reduce every 10th iteration, and min/max
+    for validation one at entry.  No V or H data ever moves.
+    """
+
+    def __init__(self, local, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.local = local
+        self.group = group
+        self.kind = local.kind
+        self.world = dist.get_world_size(group)
+
+    @property
+    def precision(self):
+        return self.local.precision
+
+    def close(self):
+        self.local.close()
+
+    def sync(self):
+        self.local.sync()
+
+    def minmax(self):
+        vmin, vmax = self.local.minmax()
+        t = torch.tensor([-vmin, vmax], dtype=torch.float32, device=self._reduce_device())
+        if vmin != vmin or vmax != vmax:          # NaN must survive the reduction
+            t.fill_(float("nan"))
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self.group)
+        t = t.cpu()
+        return -float(t[0]), float(t[1])
+
+    def _reduce_device(self):
+        dev = getattr(self.local, "device", None)
+        return dev if dev is not None else torch.device("cpu")
+
+    def update_w(self, beta, gamma, l1_reg, l2_reg):
+        buf = self.local.w_partial(beta)
+        self._dist.all_reduce(buf, op=self._dist.ReduceOp.SUM, group=self.group)
+        self.local.w_apply(buf, beta, gamma, l1_reg, l2_reg)
+
+    def update_h(self, beta, gamma, l1_reg, l2_reg):
+        self.local.update_h(beta, gamma, l1_reg, l2_reg)
+
+    def loss(self, beta):
+        t = self.local.loss_tensor(beta).clone()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())

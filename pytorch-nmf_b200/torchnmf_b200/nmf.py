@@ -1,0 +1,254 @@
+"""NMF / NMFD modules with the reference's surface and a B200-native `fit`.
+
+Mirrors the module surface of torchnmf 0.3.5 (`torchnmf/nmf.py`): `BaseComponent` (:173-292),
+`NMF` (:641-697), `NMFD` (:700-779) and `BaseComponent.fit` (:298-409).  Constructor arguments,
+parameter shapes (`W (C,R[,T])`, `H (N,R)` / `(B,R,L_in)`), `forward`, `state_dict` keys and the
+`fit` signature / return value / exceptions are the reference's.  What differs is the inside of the
+iteration loop: instead of materialising `WH` and taking two autograd backward passes
+(`_double_backward_update`, :52-92), every update is one call into libnmf_b200.so, whose fused
+sm_100a kernels never write the (N x C) reconstruction or ratio matrices to HBM.
+
+There is no CPU compute path: `fit` on CPU-resident modules copies V / W / H to the current CUDA
+device, runs there, and copies the factors back into the same Parameter storages ("host buffer"
+mode, the `e2e` number of bench.py).  Without a CUDA device or without the built library it raises.
+
+Out of scope: sparse targets, `sparse_fit`, NMF2D/NMF3D, PLCA, trainers.
+"""
+import math
+from collections.abc import Iterable as _Iterable
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn import Parameter
+
+from .constants import eps  # noqa: F401  (re-exported like torchnmf.nmf does)
+from . import engine as _engine
+
+try:
+    from tqdm import tqdm as _tqdm
+except Exception:  # pragma: no cover
+    _tqdm = None
+
+__all__ = ["BaseComponent", "NMF", "NMFD"]
+
+
+def _gamma(beta):
+    # nmf.py:341-346
+    if beta < 1:
+        return 1.0 / (2.0 - beta)
+    if beta > 2:
+        return 1.0 / (beta - 1.0)
+    return 1.0
+
+
+class _NullBar:
+    def __init__(self, *a, **k): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+    def set_postfix(self, **k): pass
+    def update(self, n): pass
+
+
+class BaseComponent(torch.nn.Module):
+    """Base class of the NMF modules (reference: nmf.py:173-292).
+
+    Args:
+        rank: size of the hidden dimension
+        W / H: a size (iterable of ints -> random non-negative init) or an initial non-negative Tensor
+        trainable_W / trainable_H: whether a *given tensor* is updated by `fit`
+    """
+
+    def __init__(self, rank=None, W=None, H=None, trainable_W=True, trainable_H=True):
+        super().__init__()
+        inferred = None
+        for name, spec, trainable in (("W", W, trainable_W), ("H", H, trainable_H)):
+            if isinstance(spec, Tensor):
+                assert torch.all(spec >= 0.), f"Tensor {name} should be non-negative."   # nmf.py:215,227
+                p = Parameter(torch.empty(*spec.size()), requires_grad=trainable)
+                p.data.copy_(spec)
+                self.register_parameter(name, p)
+                inferred = p.shape[1]
+            elif isinstance(spec, _Iterable):
+                spec = tuple(spec)
+                self.register_parameter(name, Parameter(torch.randn(*spec).abs()))       # nmf.py:221,234
+                inferred = spec[1]
+            else:
+                self.register_parameter(name, None)
+
+        if inferred is None:
+            assert rank, "A rank should be given when W and H are not available!"        # nmf.py:240
+        else:
+            if self.H is not None:
+                assert self.H.shape[1] == inferred, "Latent size of H does not match with others!"
+            if self.W is not None:
+                assert self.W.shape[1] == inferred, "Latent size of W does not match with others!"
+                self.out_channels = self.W.shape[0]
+                if self.W.ndim > 2:
+                    self.kernel_size = self.W.shape[2:]
+            rank = inferred
+        self.rank = rank
+
+    def extra_repr(self):
+        s = f"{self.rank}"
+        if self.W is not None:
+            s += f", out_channels={self.out_channels}"
+            if hasattr(self, "kernel_size"):
+                s += f", kernel_size={tuple(self.kernel_size)}"
+        return s
+
+    def forward(self, H=None, W=None):
+        """Reconstruction only (nmf.py:261-284); plain differentiable torch ops, not on the fit path."""
+        H = self.H if H is None else H
+        W = self.W if W is None else W
+        assert H is not None
+        assert W is not None
+        return self.reconstruct(H, W)
+
+    @staticmethod
+    def reconstruct(H, W):
+        raise NotImplementedError
+
+    # ---- engine selection -------------------------------------------------------------------
+    _engine_cls = None
+
+    def _build_engine(self, V, W, H, precision):
+        return self._engine_cls(V, W, H, precision)
+
+    def _check_target_shape(self, V):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
+            precision="auto", group=None, _engine_factory=None):
+        """Learn the model for `V` by minimising the beta-divergence with multiplicative updates.
+
+        Positional arguments, defaults, return value (`n_iter`) and exceptions are those of
+        `BaseComponent.fit` in the reference (nmf.py:298-409).  Keyword-only extras:
+
+        precision: "auto" | "f32" | "f16" | "f16_split" -- arithmetic of the contraction kernels
+        group:     a torch.distributed process group; V and H are then this rank's ROW shard
+                   (rows of V <-> rows of H) and W is replicated; one all-reduce per W update.
+        """
+        if V.is_sparse:
+            raise NotImplementedError("sparse targets are outside the accelerated hot path; "
+                                      "use the reference implementation for them (SURVEY.md section 8 f3)")
+        W, H = self.W, self.H
+        assert W is not None and H is not None, "fit() needs both W and H"
+        self._check_target_shape(V)
+
+        # ---- placement: run on the parameters' CUDA device, or stage host buffers through cuda ----
+        staged = False
+        if _engine_factory is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("torchnmf_b200.fit needs a CUDA device (sm_100a); there is no CPU fallback")
+            if W.device.type == "cuda":
+                dev = W.device
+                Vd = V.to(dev, non_blocking=True).contiguous()
+                Wd, Hd = W.data, H.data
+            else:
+                staged = True
+                dev = torch.device("cuda", torch.cuda.current_device())
+                Vd = V.to(dev, non_blocking=True).contiguous()
+                Wd = W.data.to(dev, non_blocking=True).contiguous()
+                Hd = H.data.to(dev, non_blocking=True).contiguous()
+            if not Wd.is_contiguous() or not Hd.is_contiguous():
+                raise ValueError("W and H must be contiguous")
+            eng = self._build_engine(Vd, Wd, Hd, precision)
+        else:
+            eng = _engine_factory(V, W.data, H.data)
+        if group is not None:
+            if eng.kind != "nmf":
+                raise NotImplementedError("row sharding is implemented for NMF only (NMFD: replicas only)")
+            eng = _engine.ShardedEngine(eng, group)
+
+        try:
+            vmin, vmax = eng.minmax()
+            assert vmin >= 0., "Target should be non-negative."                            # nmf.py:329-330
+            if vmin == 0 and beta <= 0:                                                    # nmf.py:332-336
+                raise ValueError("When beta <= 0 and V contains zeros, the training process may diverge. "
+                                 "Please add small values to V, or use a positive beta value.")
+            gamma = _gamma(beta)
+            l1_reg = alpha * l1_ratio                                                      # nmf.py:348
+            l2_reg = alpha * (1 - l1_ratio)                                                # nmf.py:349
+
+            def fit_loss():
+                d = eng.loss(beta)
+                return math.sqrt(2.0 * d) if d >= 0 else float("nan")                      # nmf.py:362,402
+
+            loss_init = fit_loss()
+            previous_loss = loss_init
+            train_w, train_h = W.requires_grad, H.requires_grad
+            bar = _tqdm(total=max_iter, disable=not verbose) if _tqdm is not None else _NullBar()
+            n_iter = -1
+            with bar as pbar:
+                for n_iter in range(max_iter):                                             # nmf.py:366
+                    if train_w:
+                        eng.update_w(beta, gamma, l1_reg, l2_reg)                          # nmf.py:367-378
+                    if train_h:
+                        eng.update_h(beta, gamma, l1_reg, l2_reg)                          # nmf.py:380-391
+                    if n_iter % 10 == 9:                                                   # nmf.py:393
+                        loss = fit_loss()
+                        pbar.set_postfix(loss=loss)
+                        pbar.update(10)
+                        if (previous_loss - loss) / loss_init < tol:                       # nmf.py:405
+                            break
+                        previous_loss = loss
+            if staged:
+                W.data.copy_(Wd)
+                H.data.copy_(Hd)
+            self.last_fit_precision = eng.precision
+        finally:
+            eng.close()
+        return n_iter + 1                                                                  # nmf.py:409
+
+
+class NMF(BaseComponent):
+    """Non-negative matrix factorisation  V (N,C) ~= H (N,R) @ W (C,R)^T   (reference: nmf.py:641-697)."""
+    _engine_cls = _engine.CudaNmfEngine
+
+    def __init__(self, Vshape=None, rank=None, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            M, K = Vshape                                  # wrong arity raises, as in the reference (:684)
+            rank = rank if rank else K
+            kwargs["W"] = (K, rank)
+            kwargs["H"] = (M, rank)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W):
+        return F.linear(H, W)                              # H @ W^T, nmf.py:691-693
+
+    def _check_target_shape(self, V):
+        if V.dim() != 2 or V.shape[0] != self.H.shape[0] or V.shape[1] != self.W.shape[0]:
+            raise RuntimeError(f"target shape {tuple(V.shape)} does not match H {tuple(self.H.shape)} / "
+                               f"W {tuple(self.W.shape)}")
+
+
+class NMFD(BaseComponent):
+    """Non-negative matrix factor deconvolution (reference: nmf.py:700-779).
+
+    V (B,C,L) ~= sum_t W[:,:,t] @ shift_t(H),  W (C,R,T), H (B,R,L-T+1).
+    """
+    _engine_cls = _engine.CudaNmfdEngine
+
+    def __init__(self, Vshape=None, rank=None, T=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            if isinstance(T, _Iterable):
+                T, = T
+            batch, K, M = Vshape                           # wrong arity raises, as in the reference (:769)
+            rank = rank if rank else K
+            kwargs["W"] = (K, rank, T)
+            kwargs["H"] = (batch, rank, M - T + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W):
+        return F.conv1d(H, W.flip(2), padding=W.shape[2] - 1)   # nmf.py:776-779
+
+    def _check_target_shape(self, V):
+        ok = (V.dim() == 3 and V.shape[0] == self.H.shape[0] and V.shape[1] == self.W.shape[0]
+              and V.shape[2] == self.H.shape[2] + self.W.shape[2] - 1)
+        if not ok:
+            raise RuntimeError(f"target shape {tuple(V.shape)} does not match H {tuple(self.H.shape)} / "
+                               f"W {tuple(self.W.shape)}")

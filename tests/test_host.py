@@ -1,0 +1,144 @@
+"""CPU-side tests: module surface (mirrors reference tests/test_nmf.py:8-69), the C-ABI library's
+symbols, loud failure without CUDA, and the host logic of fit() driven by an oracle-backed engine."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import mu_oracle as orc
+from torchnmf_b200 import NMF, NMFD, BaseComponent, _capi
+from oracle_engine import OracleNmfEngine, OracleNmfdEngine
+
+CASES = load_golden()
+
+
+# ---- constructor validity matrix: reference tests/test_nmf.py:8-37 ------------------------------
+@pytest.mark.parametrize("W", [(50, 8), torch.rand(50, 8), None])
+@pytest.mark.parametrize("H", [(100, 8), torch.rand(100, 8), None])
+def test_base_valid_construct(W, H):
+    m = BaseComponent(8, W, H)
+    assert (m.H is None) == (H is None)
+    assert (m.W is None) == (W is None)
+
+
+@pytest.mark.parametrize("rank, W, H", [
+    (None, None, None),
+    (None, (50, 8), (100, 10)),
+    (None, torch.rand(50, 8), (100, 10)),
+    (None, -torch.rand(50, 8) - 1, (100, 8)),
+    (None, (50, 8), torch.rand(100, 10)),
+    (None, (50, 8), -torch.rand(100, 8) - 1),
+    (None, torch.rand(50, 8), torch.rand(100, 10)),
+])
+def test_base_invalid_construct(rank, W, H):
+    with pytest.raises(Exception):
+        BaseComponent(rank, W, H)
+
+
+def test_shapes_and_repr():
+    # reference tests/test_nmf.py:40-69
+    m = NMF((100, 50))
+    assert m().shape == (100, 50) and m.rank == 50
+    m = NMF((20, 30), 5)
+    assert m.W.shape == (30, 5) and m.H.shape == (20, 5)
+    assert "out_channels=30" in repr(m)
+    d = NMFD((100, 50, 100))
+    assert d().shape == (100, 50, 100)
+    d = NMFD((1, 33, 50), 16, 3)
+    assert d.W.shape == (33, 16, 3) and d.H.shape == (1, 16, 48) and d().shape == (1, 33, 50)
+    for bad in [(100, 50, 50), (100,)]:
+        with pytest.raises(Exception):
+            NMF(bad)
+    for bad in [(100, 50), (100,), (100, 50) * 2]:
+        with pytest.raises(Exception):
+            NMFD(bad)
+
+
+def test_given_tensor_is_copied_and_trainable_flag():
+    W0 = torch.rand(30, 4)
+    m = NMF(W=W0, H=(20, 4), trainable_W=False)
+    assert m.W.data_ptr() != W0.data_ptr() and torch.equal(m.W.data, W0)
+    assert not m.W.requires_grad and m.H.requires_grad
+    sd = m.state_dict()
+    assert set(sd) == {"W", "H"}
+
+
+def test_forward_accepts_external_factors_and_autograd():
+    m = NMF(W=(30, 4), rank=4)           # H is None: module used as a layer (tests/test_trainer.py:17-18)
+    H = torch.rand(7, 4, requires_grad=True)
+    out = m(H=H)
+    out.sum().backward()
+    assert out.shape == (7, 30) and H.grad is not None
+
+
+# ---- the C-ABI library ---------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nmf_b200.h")).read()
+    declared = set(re.findall(r"\b(nmfb200_[a-z0-9_]+)\s*\(", header))
+    declared.discard("nmfb200_ctx")
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _capi.load().nmfb200_abi_version() == 1
+
+
+def test_library_rejects_bad_arguments_without_gpu_work():
+    lib = _capi.load()
+    ctx = ctypes.c_void_p()
+    assert lib.nmfb200_nmf_create(None, 0, 4, 4, 2, 0) != 0
+    assert lib.nmfb200_nmf_create(ctypes.byref(ctx), 0, 0, 4, 2, 0) != 0
+    assert b"positive" in lib.nmfb200_last_error()
+    assert lib.nmfb200_nmf_create(ctypes.byref(ctx), 0, 4, 4, 2, 77) != 0
+    assert lib.nmfb200_nmf_w_partial_numel(None, 1.0) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the loud failure on a CUDA-less host")
+def test_fit_fails_loudly_without_cuda():
+    m = NMF((10, 8), 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.fit(torch.rand(10, 8))
+
+
+def test_sparse_target_is_refused():
+    m = NMF((10, 8), 3)
+    with pytest.raises(NotImplementedError):
+        m.fit(torch.rand(10, 8).to_sparse())
+
+
+# ---- fit() host logic against the reference's outputs, with the oracle standing in for the GPU ----
+@pytest.mark.parametrize("name", ["nmf_b1_a0_l0", "nmf_b0.5_a0.1_l0.5", "nmf_b3_a0_l0", "nmf_stoprule",
+                                  "nmf_frozenW", "nmfd_b1_a0_l0", "nmfd_b0_a0.1_l0.5"])
+def test_fit_loop_matches_reference(name):
+    c = CASES[name]
+    cls, eng = (NMF, OracleNmfEngine) if c["kind"] == "nmf" else (NMFD, OracleNmfdEngine)
+    m = cls(W=c["W0"], H=c["H0"], trainable_W=bool(c.get("trainable_W", 1)))
+    n_iter = m.fit(c["V"], c["beta"], c["tol"], int(c["max_iter"]), False, c["alpha"], c["l1_ratio"],
+                   _engine_factory=eng)
+    assert n_iter == c["n_iter"]
+    assert torch.allclose(m.W.data, c["W"], rtol=5e-5, atol=1e-7)
+    assert torch.allclose(m.H.data, c["H"], rtol=5e-5, atol=1e-7)
+
+
+def test_fit_validation_errors():
+    V = torch.rand(12, 9)
+    m = NMF(V.shape, 3)
+    Vneg = V.clone(); Vneg[0, 0] = -1
+    with pytest.raises(AssertionError, match="non-negative"):
+        m.fit(Vneg, _engine_factory=OracleNmfEngine)
+    Vz = V.clone(); Vz[0, 0] = 0
+    with pytest.raises(ValueError, match="beta <= 0"):
+        m.fit(Vz, beta=0, _engine_factory=OracleNmfEngine)
+    with pytest.raises(RuntimeError, match="does not match"):
+        m.fit(torch.rand(5, 5), _engine_factory=OracleNmfEngine)
+
+
+def test_fit_returns_niter_plus_one_and_verbose_runs():
+    V = torch.rand(20, 10)
+    m = NMF(V.shape, 3)
+    assert m.fit(V, 1, float("-inf"), 7, True, _engine_factory=OracleNmfEngine) == 7
+    assert not torch.isnan(m.W).any() and not torch.isnan(m.H).any()
