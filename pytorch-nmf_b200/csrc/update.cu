@@ -102,6 +102,10 @@ reduce_chunks_kernel(const float* __restrict__ src, int nchunks, int64_t chunk_s
   dst[idx] = t;
 }
 
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? NAN : fmaxf(a, b); }
+
+// NaN-sticky min / max so that a NaN in V fails fit()'s non-negativity assertion like torch.all(V >= 0) does
 __global__ void __launch_bounds__(256)
 minmax_stage1(const float* __restrict__ V, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ scratch) {
   __shared__ float smin[8], smax[8];
@@ -110,22 +114,17 @@ minmax_stage1(const float* __restrict__ V, int64_t rows, int64_t cols, int64_t l
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     int64_t r = i / cols, c = i - r * cols;
     float v = V[r * ld + c];
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
-    if (v != v) { mn = v; mx = v; }       // propagate NaN so the non-negativity assertion fails
+    mn = nan_min(mn, v);
+    mx = nan_max(mx, v);
   }
   for (int o = 16; o > 0; o >>= 1) {
-    float a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-    mn = (a != a) ? a : fminf(mn, a);
-    mx = (b != b) ? b : fmaxf(mx, b);
+    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
   if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; ++k) {
-      mn = (smin[k] != smin[k]) ? smin[k] : fminf(mn, smin[k]);
-      mx = (smax[k] != smax[k]) ? smax[k] : fmaxf(mx, smax[k]);
-    }
+    for (int k = 1; k < 8; ++k) { mn = nan_min(mn, smin[k]); mx = nan_max(mx, smax[k]); }
     scratch[blockIdx.x] = mn;
     scratch[1024 + blockIdx.x] = mx;
   }
@@ -134,11 +133,7 @@ minmax_stage1(const float* __restrict__ V, int64_t rows, int64_t cols, int64_t l
 __global__ void minmax_stage2(const float* __restrict__ scratch, int nb, float* __restrict__ mm) {
   if (threadIdx.x != 0) return;
   float mn = INFINITY, mx = -INFINITY;
-  for (int k = 0; k < nb; ++k) {
-    float a = scratch[k], b = scratch[1024 + k];
-    mn = (a != a) ? a : fminf(mn, a);
-    mx = (b != b) ? b : fmaxf(mx, b);
-  }
+  for (int k = 0; k < nb; ++k) { mn = nan_min(mn, scratch[k]); mx = nan_max(mx, scratch[1024 + k]); }
   mm[0] = mn;
   mm[1] = mx;
 }

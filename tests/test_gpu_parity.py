@@ -155,3 +155,98 @@ def test_kl_update_preserves_marginals_and_decreases_loss(precision):
         assert cur <= prev * (1 + 1e-5), (it, cur, prev)
         prev = cur
     eng.close()
+
+
+# ---- tensor-core (tcgen05) path -------------------------------------------------------------------------
+TC_RTOL, TC_ATOL_REL = 1e-3, 1e-5     # north_star: rtol 1e-3 (atol = 1e-5 * max|x| for near-zero entries)
+
+
+@pytest.mark.parametrize("name", ["nmf_tc", "nmf_tcragged"])
+@pytest.mark.parametrize("precision", ["f16", "f16_split"])
+def test_tc_path_matches_reference_golden(name, precision):
+    c = CASES[name]
+    m, n_iter = _run_case(c, precision)
+    assert m.last_fit_precision == precision
+    assert n_iter == c["n_iter"]
+    for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
+        ok, err = _close(got, want, TC_RTOL, TC_ATOL_REL)
+        assert ok, f"{name} {precision} {nm}: scaled err {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (1000, 700, 20), (130, 2049, 33), (257, 129, 1), (4096, 1024, 64)])
+@pytest.mark.parametrize("precision", ["f16", "f16_split"])
+def test_tc_single_updates_match_oracle(shape, precision):
+    N, C, R = shape
+    torch.manual_seed(N + C + R)
+    V = torch.rand(N, C)
+    W0 = torch.rand(C, R) + 0.05
+    H0 = torch.rand(N, R) * 3
+    from torchnmf_b200.engine import CudaNmfEngine
+    Wd, Hd = W0.cuda(), H0.cuda()
+    eng = CudaNmfEngine(V.cuda(), Wd, Hd, precision)
+    eng.update_w(1, 1.0, 0.0, 0.0)
+    Wn = orc.nmf_update_w(V, W0, H0, 1)
+    eng.update_h(1, 1.0, 0.01, 0.02)
+    Hn = orc.nmf_update_h(V, Wn, H0, 1, 1.0, 0.01, 0.02)
+    eng.close()
+    # one update: only the fp16 rounding of V / P / factors separates the two (V here is NOT fp16-exact)
+    assert _close(Wd.cpu(), Wn, 1e-3, 1e-5)[0], _close(Wd.cpu(), Wn, 1e-3, 1e-5)[1]
+    assert _close(Hd.cpu(), Hn, 1e-3, 1e-5)[0], _close(Hd.cpu(), Hn, 1e-3, 1e-5)[1]
+
+
+def test_tc_handles_extreme_scales():
+    # power-of-two rescaling of the fp16 operand copies: results must be scale-covariant
+    torch.manual_seed(11)
+    V = torch.rand(256, 384)
+    W0 = torch.rand(384, 32) + 0.1
+    H0 = torch.rand(256, 32) + 0.1
+    outs = []
+    for sv, sw in ((1.0, 1.0), (1e-3, 1e4), (300.0, 1e-5)):
+        m = NMF(W=W0 * sw, H=H0).cuda()
+        m.fit((V * sv).cuda(), 1, float("-inf"), 5, precision="f16_split")
+        outs.append((m.W.data.cpu() @ m.H.data.cpu().t()) / sv)
+        assert not torch.isnan(outs[-1]).any()
+    # after a few KL iterations the reconstruction H W^T no longer depends on the initial scale of W
+    # (up to eps effects, which are absolute): compare reconstructions
+    assert torch.allclose(outs[0], outs[1], rtol=5e-3, atol=1e-4)
+
+
+def test_tc_sharded_pieces_match_full_update():
+    torch.manual_seed(12)
+    N, C, R = 1024, 512, 64
+    V = torch.rand(N, C).bfloat16().float(); W0 = torch.rand(C, R) + 0.1; H0 = torch.rand(N, R) + 0.1
+    from torchnmf_b200.engine import CudaNmfEngine
+    full_W = W0.cuda(); full_H = H0.cuda()
+    eng = CudaNmfEngine(V.cuda(), full_W, full_H, "f16_split")
+    eng.update_w(1, 1.0, 0.0, 0.0); eng.close()
+    parts = []
+    Ws = W0.cuda()
+    engs = []
+    for lo, hi in ((0, 600), (600, N)):
+        e = CudaNmfEngine(V[lo:hi].cuda().contiguous(), Ws, H0[lo:hi].cuda().contiguous(), "f16_split")
+        parts.append(e.w_partial(1)); engs.append(e)
+    red = parts[0] + parts[1]
+    engs[0].w_apply(red, 1, 1.0, 0.0, 0.0)
+    for e in engs: e.close()
+    assert torch.allclose(Ws.cpu(), full_W.cpu(), rtol=2e-4, atol=1e-7)
+
+
+def test_cfg2_200_iterations_match_reference_subsample():
+    """BASELINE.json configs[1] at full size: 200 KL iterations from seeds 0/1 vs the reference's own CPU
+    result (tests/golden/nmf_cfg2_kl_200.npz, generated by oracle/make_golden.py --cfg2)."""
+    z = np.load(f"{GOLDEN}/nmf_cfg2_kl_200.npz")
+    N, C, R = 65536, 4096, 64
+    torch.manual_seed(0)
+    V = torch.rand(N, C).bfloat16().float()
+    torch.manual_seed(1)
+    W0 = torch.randn(C, R).abs(); H0 = torch.randn(N, R).abs()
+    assert math.isclose(V.double().sum().item(), float(z["v_sum"]), rel_tol=1e-12)      # same inputs as the fixture
+    assert math.isclose(H0.double().sum().item(), float(z["h0_sum"]), rel_tol=1e-12)
+    m = NMF(W=W0, H=H0).cuda()
+    n = m.fit(V.cuda(), 1, float("-inf"), int(z["iters"]))
+    assert n == int(z["n_iter"])
+    Wg, Hg = torch.from_numpy(z["W_sub"]), torch.from_numpy(z["H_sub"])
+    W, H = m.W.data.cpu()[::8], m.H.data.cpu()[::128]
+    for got, want, mx, nm in ((W, Wg, float(z["w_absmax"]), "W"), (H, Hg, float(z["h_absmax"]), "H")):
+        err = ((got - want).abs() / (want.abs() + TC_ATOL_REL * mx / TC_RTOL)).max().item()
+        assert torch.allclose(got, want, rtol=TC_RTOL, atol=TC_ATOL_REL * mx), f"{nm} [{m.last_fit_precision}]: {err / TC_RTOL:.2f} x tol"
