@@ -128,16 +128,17 @@ def timed_steps(fn, steps, warmup, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[-1])
+    timed_steps.per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,6 +270,7 @@ def main():
     l0 = _capi.launch_count()
     ms = timed_steps(step_resident, a.steps, 0, world)
     launches = _capi.launch_count() - l0
+    per_step = list(getattr(timed_steps, "per_step", []))
     clocks = sampler.stop() if sampler else None
     precision = model.last_fit_precision
     value = a.iters * a.steps * world / (ms * 1e-3)
@@ -349,7 +351,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "MU iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "step_ms": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"f32": "f32", "f16": "f16", "f16_split": "f16"}.get(precision, precision),
             "data": "synthetic",
             "config": {"workload": desc, "N_per_gpu": N, "C": C, "R": R, "beta": beta, "iters_per_step": a.iters,

@@ -5,21 +5,24 @@
 //
 //   TMA      G tile [128 c][KW] and V tile [128 m][128 c] (fp16, SWIZZLE_128B) -> shared memory
 //   MMA-1    S[128 m][128 c]  = F_blk G_tile^T            tcgen05.mma SS, fp32 accumulators in TMEM
-//   ratio    P = V * rcp(S*c1 + c2)  (== V / (F G^T + eps), nmf.py:65) -> fp16, written back to TMEM
-//            over the S columns it was computed from (128 threads per tile, one TMEM lane each)
-//   MMA-2    O[128 m][KW]   += P G_tile                    tcgen05.mma TS (A = P from TMEM, B = G tile MN-major)
+//   ratio    P = V * rcp(S*c1 + c2)  (== V / (F G^T + eps), nmf.py:65); the CENTRED tile P - kappa -> fp16, written
+//            back to TMEM over the S columns it was computed from (128 threads per tile, one TMEM lane each)
+//   MMA-2    O[128 m][KW]   += (P - kappa) G_tile          tcgen05.mma TS (A from TMEM, B = G tile MN-major)
+//            (numerator = O + kappa colsum(G), added in fp32 by the ratio stage)
 //
 // so neither S = WH nor P = V/(WH) ever leaves the SM (nmf.py:376-378 materialises both in HBM).
 // F/G are fp16 copies of the factors scaled by a power of two; in split mode they carry hi|lo halves
 // (KW = 2*Rp) and S = Fhi Ghi + Flo Ghi + Fhi Glo, O = P [Ghi|Glo] recovers ~22-bit factors.
 //
-// Warp roles (448 threads): 0 TMA producer | 1 MMA issuer (one lane) | 2-5 ratio warpgroup A (even
-// tiles) | 6-9 ratio warpgroup B (odd tiles) | 10-13 epilogue (O -> fp32 partial numerators).
+// Warp roles (512 threads): 0 TMA producer for V (the HBM stream, own ring) | 1 MMA issuer (one lane) |
+// 2 TMA producer for F/G (L2-resident factors) | 4-7 ratio warpgroup A (even tiles) | 8-11 ratio warpgroup B
+// (odd tiles) | 12-15 epilogue (O -> fp32 partial numerators).  S runs two tiles ahead of O in the tensor pipe.
 #include "tc_nmf.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "sm100_ptx.cuh"
@@ -30,10 +33,11 @@ namespace {
 
 constexpr int kRp = 64;              // padded rank handled by this kernel
 constexpr int kTileM = 128, kTileN = 128;
-constexpr int kThreads = 448;
+constexpr int kThreads = 512;
+constexpr int kSStages = 3;           // S/P accumulator stages in TMEM
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0;        // two S/P stages: columns [0,128) and [128,256)
-constexpr uint32_t kColO = 256;      // O accumulator: [256, 256 + KW)
+constexpr uint32_t kColS = 0;        // S/P stages: columns [128 i, 128 i + 128)
+constexpr uint32_t kColO = 128 * kSStages;   // O accumulator: [384, 384 + KW)
 
 struct TcKernelParams {
   int Mr, Nc;                 // valid rows of F / rows of G (= columns of Vm)
@@ -41,30 +45,34 @@ struct TcKernelParams {
   float* part;                // [nchunks][Mr][ldp] fp32 numerators
   int64_t chunk_stride;
   int ldp;
-  const int* exps;            // device: {v, aW, aH} power-of-two exponents of the fp16 copies
+  const int* exps;            // device: {v, aW, aH, p}: power-of-two exponents of V16, W16, H16 and of the ratio tile P
   int ef, eg;                 // which of exps[] belong to F and G
+  double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
+  const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
 };
 
-template <int KW, int NST>
+// shared memory: NF F blocks | NG G-tile ring | NV V-tile ring | mbarriers | tmem ptr | loss slots
+template <int KW, int NF, int NG, int NV>
 struct SmemLayout {
   static constexpr int kFBytes = kTileM * KW * 2;
   static constexpr int kGBytes = kTileN * KW * 2;
   static constexpr int kVBytes = kTileM * kTileN * 2;
   static constexpr int kF = 0;
-  static constexpr int kG = kF + 2 * kFBytes;
-  static constexpr int kV = kG + NST * kGBytes;
-  static constexpr int kBar = kV + NST * kVBytes;
-  // barriers: f_full[2] f_empty[2] gv_full[NST] g_empty[NST] v_empty[NST] s_full[2] p_full[2] o_full o_empty
-  static constexpr int kNumBars = 4 + 3 * NST + 6;
+  static constexpr int kG = kF + NF * kFBytes;
+  static constexpr int kV = kG + NG * kGBytes;
+  static constexpr int kBar = kV + NV * kVBytes;
+  static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 2 * kSStages + 2;
   static constexpr int kTmemPtr = kBar + 8 * kNumBars;
-  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kLossSlots = kTmemPtr + 16;
+  static constexpr int kTotal = kLossSlots + 16 * 8;
 };
 
-template <int KW, int NST, bool SPLIT>
+template <int KW, int NF, int NG, int NV, bool SPLIT, bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
-  using L = SmemLayout<KW, NST>;
+  using L = SmemLayout<KW, NF, NG, NV>;
+  static_assert(kSStages * 128 + KW <= (int)kTmemCols, "TMEM budget");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw32 = ptx::smem_u32(smem_raw);
   const uint32_t sbase = (raw32 + 1023u) & ~1023u;
@@ -72,21 +80,20 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   const uint32_t sF = sbase + L::kF, sG = sbase + L::kG, sV = sbase + L::kV;
   const uint32_t bar0 = sbase + L::kBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  const int B_FFULL = 0, B_FEMPTY = 2, B_GVFULL = 4, B_GEMPTY = 4 + NST, B_VEMPTY = 4 + 2 * NST,
-            B_SFULL = 4 + 3 * NST, B_PFULL = B_SFULL + 2, B_OFULL = B_PFULL + 2, B_OEMPTY = B_OFULL + 1;
+  constexpr int B_FFULL = 0, B_FEMPTY = NF, B_GFULL = 2 * NF, B_GEMPTY = B_GFULL + NG, B_VFULL = B_GEMPTY + NG,
+                B_VEMPTY = B_VFULL + NV, B_SFULL = B_VEMPTY + NV, B_PFULL = B_SFULL + kSStages,
+                B_OFULL = B_PFULL + kSStages, B_OEMPTY = B_OFULL + 1;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + L::kTmemPtr);
+  double* loss_slots = reinterpret_cast<double*>(smem_al + L::kLossSlots);      // [8 ratio warps][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmF); ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(B_FFULL + i), 1); ptx::mbar_init(BAR(B_FEMPTY + i), 1); }
-    for (int i = 0; i < NST; ++i) {
-      ptx::mbar_init(BAR(B_GVFULL + i), 1);
-      ptx::mbar_init(BAR(B_GEMPTY + i), 1);
-      ptx::mbar_init(BAR(B_VEMPTY + i), 128);
-    }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128); }
+    for (int i = 0; i < NF; ++i) { ptx::mbar_init(BAR(B_FFULL + i), 1); ptx::mbar_init(BAR(B_FEMPTY + i), 1); }
+    for (int i = 0; i < NG; ++i) { ptx::mbar_init(BAR(B_GFULL + i), 1); ptx::mbar_init(BAR(B_GEMPTY + i), 1); }
+    for (int i = 0; i < NV; ++i) { ptx::mbar_init(BAR(B_VFULL + i), 1); ptx::mbar_init(BAR(B_VEMPTY + i), 128); }
+    for (int i = 0; i < kSStages; ++i) { ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128); }
     ptx::mbar_init(BAR(B_OFULL), 1);
     ptx::mbar_init(BAR(B_OEMPTY), 128);
     ptx::fence_barrier_init();
@@ -104,28 +111,42 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   const int total_items = p.row_blocks * p.nchunks;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer: V tiles (the HBM stream) =================================
+    if (lane == 0) {
+      uint32_t t = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int rb = item % p.row_blocks, chunk = item / p.row_blocks;
+        const int tb = chunk * p.tiles_per_chunk;
+        const int te = min(p.tiles, tb + p.tiles_per_chunk);
+        for (int j = tb; j < te; ++j, ++t) {
+          const uint32_t s = t % NV, ph = (t / NV) & 1;
+          ptx::mbar_wait(BAR(B_VEMPTY + s), ph ^ 1);
+          ptx::mbar_expect_tx(BAR(B_VFULL + s), L::kVBytes);
+          for (int vb = 0; vb < 2; ++vb)
+            ptx::tma_load_2d(&tmV, BAR(B_VFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * kTileN + vb * 64,
+                             rb * kTileM);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== TMA producer: F blocks and G tiles (L2-resident factors) ================
     if (lane == 0) {
       uint32_t it = 0, t = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int rb = item % p.row_blocks, chunk = item / p.row_blocks;
         const int tb = chunk * p.tiles_per_chunk;
         const int te = min(p.tiles, tb + p.tiles_per_chunk);
-        const uint32_t fb = it & 1;
-        ptx::mbar_wait(BAR(B_FEMPTY + fb), ((it >> 1) & 1) ^ 1);
+        const uint32_t fb = it % NF;
+        ptx::mbar_wait(BAR(B_FEMPTY + fb), ((it / NF) & 1) ^ 1);
         ptx::mbar_expect_tx(BAR(B_FFULL + fb), L::kFBytes);
         for (int kb = 0; kb < KW / 64; ++kb)
           ptx::tma_load_2d(&tmF, BAR(B_FFULL + fb), sF + fb * L::kFBytes + kb * (kTileM * 128), kb * 64, rb * kTileM);
         for (int j = tb; j < te; ++j, ++t) {
-          const uint32_t s = t % NST, ph = (t / NST) & 1;
+          const uint32_t s = t % NG, ph = (t / NG) & 1;
           ptx::mbar_wait(BAR(B_GEMPTY + s), ph ^ 1);
-          ptx::mbar_wait(BAR(B_VEMPTY + s), ph ^ 1);
-          ptx::mbar_expect_tx(BAR(B_GVFULL + s), L::kGBytes + L::kVBytes);
+          ptx::mbar_expect_tx(BAR(B_GFULL + s), L::kGBytes);
           for (int kb = 0; kb < KW / 64; ++kb)
-            ptx::tma_load_2d(&tmG, BAR(B_GVFULL + s), sG + s * L::kGBytes + kb * (kTileN * 128), kb * 64, j * kTileN);
-          for (int vb = 0; vb < 2; ++vb)
-            ptx::tma_load_2d(&tmV, BAR(B_GVFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * kTileN + vb * 64,
-                             rb * kTileM);
+            ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (kTileN * 128), kb * 64, j * kTileN);
         }
       }
     }
@@ -143,14 +164,16 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const int tb = chunk * p.tiles_per_chunk;
         const int te = min(p.tiles, tb + p.tiles_per_chunk);
         const int n = te - tb;
-        const uint32_t fb = it & 1;
-        ptx::mbar_wait(BAR(B_FFULL + fb), (it >> 1) & 1);
+        const uint32_t fb = it % NF;
+        ptx::mbar_wait(BAR(B_FFULL + fb), (it / NF) & 1);
         ptx::tc_fence_after();
         const uint32_t fbase = sF + fb * L::kFBytes;
 
+        // S stage of tile tt is free once O(tt - kSStages) consumed its P: that MMA was issued earlier by this
+        // thread, and the tensor pipe executes in issue order.
         auto issue_S = [&](uint32_t tt) {
-          const uint32_t s = tt % NST, st = tt & 1;
-          ptx::mbar_wait(BAR(B_GVFULL + s), (tt / NST) & 1);
+          const uint32_t s = tt % NG, st = tt % kSStages;
+          ptx::mbar_wait(BAR(B_GFULL + s), (tt / NG) & 1);
           ptx::tc_fence_after();
           const uint32_t gbase = sG + s * L::kGBytes;
           uint32_t acc = 0;
@@ -169,8 +192,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           ptx::mma_commit(BAR(B_SFULL + st));
         };
         auto issue_O = [&](uint32_t tt, bool first, bool last) {
-          const uint32_t s = tt % NST, st = tt & 1;
-          ptx::mbar_wait(BAR(B_PFULL + st), (tt >> 1) & 1);
+          const uint32_t s = tt % NG, st = tt % kSStages;
+          ptx::mbar_wait(BAR(B_PFULL + st), (tt / kSStages) & 1);
           if (first) ptx::mbar_wait(BAR(B_OEMPTY), (it & 1) ^ 1);
           ptx::tc_fence_after();
           const uint32_t gbase = sG + s * L::kGBytes;
@@ -185,24 +208,44 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           if (last) ptx::mma_commit(BAR(B_OFULL));
         };
 
-        issue_S(t);
+        // software pipeline: S runs (kSStages - 1) tiles ahead of O
+        constexpr int kAhead = kSStages - 1;
+        for (int j = 0; j < kAhead && j < n; ++j) issue_S(t + j);
+        if (n <= kAhead) ptx::mma_commit(BAR(B_FEMPTY + fb));
         for (int j = 0; j < n; ++j) {
-          if (j + 1 < n) issue_S(t + j + 1);
-          else ptx::mma_commit(BAR(B_FEMPTY + fb));
-          issue_O(t + j, j == 0, j == n - 1);
+          if (j + kAhead < n) {
+            issue_S(t + j + kAhead);
+            if (j + kAhead == n - 1) ptx::mma_commit(BAR(B_FEMPTY + fb));   // last S of the item issued
+          }
+          if (LOSS) {
+            const uint32_t tt = t + j;
+            ptx::mbar_wait(BAR(B_PFULL + tt % kSStages), (tt / kSStages) & 1);   // ratio warpgroup consumed S(tt)
+            ptx::mbar_arrive(BAR(B_GEMPTY + tt % NG));
+          } else {
+            issue_O(t + j, j == 0, j == n - 1);
+          }
         }
         t += n;
       }
     }
-  } else if (warp < 10) {
+  } else if (warp >= 4 && warp < 12) {
     // =========================== ratio warpgroups =======================
-    const int g = (warp - 2) >> 2;             // 0: even tiles, 1: odd tiles
+    const int g = (warp - 4) >> 2;             // 0: even tiles, 1: odd tiles
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int ev = p.exps[0], ea = p.exps[p.ef], eb = p.exps[p.eg];
-    const float c1 = exp2f((float)(ev - ea - eb));     // x' = S~ * 2^(v-a-b) + eps * 2^v
-    const float c2 = kEps * exp2f((float)ev);
+    const int ev = p.exps[0], ea = p.exps[p.ef], eb = p.exps[p.eg], ep = p.exps[3];
+    // update: x' = (S + eps) * 2^(v-p), so P~ = V~ / x' = P * 2^p (P ~ 1 maps to ~1: fp16-safe for any input scale)
+    // loss  : x  = S + eps in true scale
+    const float c1 = LOSS ? exp2f((float)(-ea - eb)) : exp2f((float)(ev - ea - eb - ep));
+    const float c2 = LOSS ? kEps : kEps * exp2f((float)(ev - ep));
+    // The tile fed to MMA-2 is the CENTRED ratio (P - kappa) 2^p with kappa = sum(V) / sum(W H^T) (-> 1 as the fit
+    // converges); kappa * colsum(G) is added back in fp32 by the ratio stage.  Tensor-core accumulation truncates
+    // (measured: -4.7e-5 relative on this all-positive sum, profiles/README.md), a one-signed bias that the
+    // scale-free direction (W a, H / a) of KL-NMF integrates over iterations; the centred sum is signed and
+    // small, and its fp16 rounding error is relative to |P - kappa| instead of |P|.
+    const float negpc = LOSS ? 0.f : -(*p.kappa) * exp2f((float)ep);
+    double accA = 0.0, accB = 0.0;
     uint32_t t = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int chunk = item / p.row_blocks;
@@ -212,9 +255,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       for (int j = 0; j < n; ++j) {
         const uint32_t tt = t + j;
         if ((int)(tt & 1) != g) continue;
-        const uint32_t s = tt % NST, st = tt & 1;
-        ptx::mbar_wait(BAR(B_GVFULL + s), (tt / NST) & 1);      // V tile landed (TMA -> this thread)
-        ptx::mbar_wait(BAR(B_SFULL + st), (tt >> 1) & 1);       // S tile complete
+        const uint32_t s = tt % NV, st = tt % kSStages;
+        ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);              // V tile landed (TMA -> this thread)
+        ptx::mbar_wait(BAR(B_SFULL + st), (tt / kSStages) & 1);       // S tile complete
         ptx::tc_fence_after();
         const uint32_t vrow = sV + s * L::kVBytes + row * 128;
 #pragma unroll
@@ -231,33 +274,53 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
                          : "r"(vsub + (chunk16 << 4)));
           }
           ptx::tc_wait_ld();
-          uint32_t preg[16];
           const uint32_t* vw = reinterpret_cast<const uint32_t*>(vv);
+          if (LOSS) {
+            float la = 0.f, lb = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __half2 hv = *reinterpret_cast<const __half2*>(&vw[i]);
-            const float2 vf = __half22float2(hv);
-            const float x0 = fmaf(__uint_as_float(sreg[2 * i]), c1, c2);
-            const float x1 = fmaf(__uint_as_float(sreg[2 * i + 1]), c1, c2);
-            const float p0 = vf.x * ptx::rcp_approx(x0);
-            const float p1 = vf.y * ptx::rcp_approx(x1);
-            preg[i] = ptx::pack_f16x2_sat(p0, p1);
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+              const float s0 = __uint_as_float(sreg[2 * i]), s1 = __uint_as_float(sreg[2 * i + 1]);
+              la = fmaf(vf.x, __log2f(fmaf(s0, c1, c2)), la);
+              la = fmaf(vf.y, __log2f(fmaf(s1, c1, c2)), la);
+              lb += s0 + s1;
+            }
+            accA += (double)la;
+            accB += (double)lb;
+          } else {
+            uint32_t preg[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+              const float x0 = fmaf(__uint_as_float(sreg[2 * i]), c1, c2);
+              const float x1 = fmaf(__uint_as_float(sreg[2 * i + 1]), c1, c2);
+              const float p0 = fmaf(vf.x, ptx::rcp_approx(x0), negpc);
+              const float p1 = fmaf(vf.y, ptx::rcp_approx(x1), negpc);
+              preg[i] = ptx::pack_f16x2_sat(p0, p1);
+            }
+            ptx::tmem_st16(tmem + lane_addr + kColS + st * 128 + c4 * 16, preg);
           }
-          ptx::tmem_st16(tmem + lane_addr + kColS + st * 128 + c4 * 16, preg);
         }
-        ptx::tc_wait_st();
+        if (!LOSS) ptx::tc_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(B_PFULL + st));
         ptx::mbar_arrive(BAR(B_VEMPTY + s));
       }
       t += n;
     }
-  } else {
+    if (LOSS) {
+      for (int o = 16; o > 0; o >>= 1) {
+        accA += __shfl_xor_sync(0xffffffffu, accA, o);
+        accB += __shfl_xor_sync(0xffffffffu, accB, o);
+      }
+      if (lane == 0) { loss_slots[2 * (warp - 4)] = accA; loss_slots[2 * (warp - 4) + 1] = accB; }
+    }
+  } else if (warp >= 12 && !LOSS) {
     // =========================== epilogue warpgroup =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float oscale = exp2f(-(float)p.exps[p.eg]);      // O = sum P * (G * 2^eg)
+    const float oscale = exp2f(-(float)(p.exps[p.eg] + p.exps[3]));      // O = sum (P 2^p) (G 2^eg)
     uint32_t it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int rb = item % p.row_blocks, chunk = item / p.row_blocks;
@@ -295,6 +358,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem, kTmemCols);
+  if (LOSS && threadIdx.x == 96) {          // fixed-order sum of the 8 ratio warps
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += loss_slots[2 * w]; b += loss_slots[2 * w + 1]; }
+    p.loss_part[2 * blockIdx.x] = a;
+    p.loss_part[2 * blockIdx.x + 1] = b;
+  }
 }
 
 // ---- operand preparation --------------------------------------------------------------------------
@@ -311,51 +380,187 @@ __global__ void set_vexp_kernel(const float* __restrict__ minmax, int* __restric
   if (threadIdx.x == 0 && blockIdx.x == 0) exps[0] = pow2_exp_for(minmax[1]);
 }
 
-// V (N x C fp32, ld) -> V16 (N x ldc) and Vt16 (C x ldn), both scaled by 2^exps[0].  64x64 tiles.
+__device__ __forceinline__ double block_sum256(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;     // valid in warp 0
+}
+
+// V (N x C fp32, ld) -> V16 (N x ldc) and Vt16 (C x ldn), both scaled by 2^exps[0]; 64x64 tiles.
+// Also per-block partial sums of V and V*log(V+eps) (the V-only terms of metrics.kl_div, metrics.py:22).
 __global__ void __launch_bounds__(256)
 v_to_f16_kernel(const float* __restrict__ V, int64_t ldv, int N, int C, __half* __restrict__ V16, int64_t ldc,
-                __half* __restrict__ Vt16, int64_t ldn, const int* __restrict__ exps) {
+                __half* __restrict__ Vt16, int64_t ldn, const int* __restrict__ exps, double* __restrict__ vpart) {
   __shared__ float tile[64][65];
+  __shared__ double red[8];
   const float sc = exp2f((float)exps[0]);
   const int n0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  double sv = 0.0, svl = 0.0;
   for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
     int r = idx >> 6, c = idx & 63;
-    float v = (n0 + r < N && c0 + c < C) ? V[(int64_t)(n0 + r) * ldv + c0 + c] * sc : 0.f;
+    const bool in = n0 + r < N && c0 + c < C;
+    const float raw = in ? V[(int64_t)(n0 + r) * ldv + c0 + c] : 0.f;
+    const float v = raw * sc;
     tile[r][c] = v;
-    if (n0 + r < N && c0 + c < C) V16[(int64_t)(n0 + r) * ldc + c0 + c] = __float2half_rn(v);
+    if (in) {
+      V16[(int64_t)(n0 + r) * ldc + c0 + c] = __float2half_rn(v);
+      sv += (double)raw;
+      svl += (double)(raw * logf(raw + kEps));
+    }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
     int c = idx >> 6, r = idx & 63;
     if (n0 + r < N && c0 + c < C) Vt16[(int64_t)(c0 + c) * ldn + n0 + r] = __float2half_rn(tile[r][c]);
   }
+  const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  double a = block_sum256(sv, red);
+  double b = block_sum256(svl, red);
+  if (threadIdx.x == 0) { vpart[2 * blk] = a; vpart[2 * blk + 1] = b; }
 }
+
+// vconst[0] = sum V, vconst[1] = sum V log(V + eps): fixed-order two-level reduction (single block)
+__global__ void __launch_bounds__(256)
+reduce_vconst_kernel(const double* __restrict__ vpart, int64_t nblk, double* __restrict__ vconst) {
+  __shared__ double red[8];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < nblk; i += 256) { a += vpart[2 * i]; b += vpart[2 * i + 1]; }
+  double ta = block_sum256(a, red);
+  double tb = block_sum256(b, red);
+  if (threadIdx.x == 0) { vconst[0] = ta; vconst[1] = tb; }
+}
+
+// ---- fused ratio stage for the tensor-core path (nmf.py:78-92, KL: precomputed denominator) -------------
+// grid = ceil(rows / rpb); 256 threads = 4 row groups x 64 rank lanes.  Besides the in-place update it emits
+// what the next kernels need: per-block column sums (-> KL denominator of the other factor) and the max
+// (-> power-of-two scale of the fp16 operand copy).
+struct TcApplyArgs {
+  float* param; int64_t rows; int R; int rpb;
+  const float* num; int nchunks; int64_t chunk_stride;     // pitch kRp
+  const float* kl_den; float gamma, l1, l2;
+  float* cs_part;            // [gridDim.x][64]
+  const float* kappa;        // the kernel accumulated sum (P - kappa) G: add kappa * colsum(G) back
+  unsigned int* absmax;      // slot to atomicMax into (pre-zeroed)
+  int apply;                 // 0: only emit column sums / max of the current values (dirty-factor resync)
+};
 
 __global__ void __launch_bounds__(256)
-absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ bits) {
-  float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) m = fmaxf(m, x[i]);
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
+tc_apply_kernel(TcApplyArgs a) {
+  __shared__ float sh[4][64];
+  const int r = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
+  const int64_t row1 = min(a.rows, row0 + a.rpb);
+  float cs = 0.f, mx = 0.f;
+  if (r < a.R) {
+    const float klden = a.apply ? a.kl_den[r] : 1.f;
+    const float kap = a.apply ? *a.kappa : 0.f;
+    for (int64_t row = row0 + rg; row < row1; row += 4) {
+      const int64_t idx = row * a.R + r;
+      float v = a.param[idx];
+      if (a.apply) {
+        float num = 0.f;
+        for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * kRp + r];
+        num = fmaf(kap, klden, num);                            // the kernel accumulated sum (P - kappa) G
+        const float neg = fmaxf(num, 0.f) + kEps;              // nmf.py:78
+        float pos = klden;                                      // nmf.py:368-369 / :381-382
+        if (a.l1 > 0.f) pos += a.l1;                            // nmf.py:85-86
+        if (a.l2 > 0.f) pos = fmaf(a.l2, v, pos);               // nmf.py:87-88
+        float mult = neg / pos;                                 // nmf.py:89
+        if (a.gamma != 1.0f) mult = powf(mult, a.gamma);        // nmf.py:90-91
+        v *= mult;                                              // nmf.py:92
+        a.param[idx] = v;
+      }
+      cs += v;
+      mx = fmaxf(mx, v);
+    }
+  }
+  sh[rg][r] = cs;
+  __syncthreads();
+  if (threadIdx.x < 64) a.cs_part[(int64_t)blockIdx.x * 64 + r] = (sh[0][r] + sh[1][r]) + (sh[2][r] + sh[3][r]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
 }
 
-// fp32 factor (rows x R) -> fp16 operand copy (rows x KW): [hi(0..Rp) | lo(Rp..2Rp)], scaled by 2^a where a is
-// derived from *absmax_bits; pad columns stay zero (buffer is zero-initialised once).  Writes exps[slot].
+// fp32 factor (rows x R) -> fp16 operand copy (rows x KW): [hi(0..Rp) | lo(Rp..2Rp)] scaled by 2^a, a from the
+// max found by tc_apply_kernel; pad columns stay zero (buffer zero-initialised once).  Block 0 additionally
+// finishes the column sums, publishes exps[1 + which] = a, and re-derives kappa = sum(V) / sum(W H^T) =
+// sum(V) / <colsum W, colsum H> (the typical P = V / (WH)) and the ratio-tile exponent exps[3] with kappa 2^p in [1, 2).
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-factor_to_f16_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __restrict__ out, int KW,
-                     const unsigned int* __restrict__ absmax_bits, int* __restrict__ exps, int slot) {
-  const int a = pow2_exp_for(__uint_as_float(*absmax_bits));
-  if (blockIdx.x == 0 && threadIdx.x == 0) exps[slot] = a;
+tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __restrict__ out, int KW,
+                 const unsigned int* __restrict__ absmax, unsigned int* __restrict__ absmax_next,
+                 int* __restrict__ exps, int which, const float* __restrict__ cs_part, int cs_blocks,
+                 float* __restrict__ colsum /* [2][R] */, const double* __restrict__ vconst,
+                 float* __restrict__ kappa, int center) {
+  const int a = pow2_exp_for(__uint_as_float(*absmax));
   const float sc = exp2f((float)a);
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= rows * R) return;
-  const int64_t row = idx / R;
-  const int r = (int)(idx - row * R);
-  const float xs = x[idx] * sc;
-  const __half hi = __float2half_rn(xs);
-  out[row * KW + r] = hi;
-  if (SPLIT) out[row * KW + kRp + r] = __float2half_rn(xs - __half2float(hi));
+  if (idx < rows * R) {
+    const int64_t row = idx / R;
+    const int r = (int)(idx - row * R);
+    const float xs = x[idx] * sc;
+    const __half hi = __float2half_rn(xs);
+    out[row * KW + r] = hi;
+    if (SPLIT) out[row * KW + kRp + r] = __float2half_rn(xs - __half2float(hi));
+  }
+  if (blockIdx.x == 0) {
+    // fixed-order final column sums: 4 thread groups x 64 rank lanes, 4 independent accumulators each
+    __shared__ float part4[4][64];
+    __shared__ float prod[64];
+    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = g;
+    for (; b + 12 < cs_blocks; b += 16) {
+      a0 += cs_part[(int64_t)b * 64 + r];
+      a1 += cs_part[(int64_t)(b + 4) * 64 + r];
+      a2 += cs_part[(int64_t)(b + 8) * 64 + r];
+      a3 += cs_part[(int64_t)(b + 12) * 64 + r];
+    }
+    for (; b < cs_blocks; b += 4) a0 += cs_part[(int64_t)b * 64 + r];
+    part4[g][r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const float mine = (part4[0][r] + part4[1][r]) + (part4[2][r] + part4[3][r]);
+      if (r < R) colsum[which * R + r] = mine;
+      prod[r] = r < R ? mine * colsum[(1 - which) * R + r] : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      exps[1 + which] = a;
+      *absmax_next = 0u;
+      float dot = 0.f;
+      for (int k = 0; k < 64; ++k) dot += prod[k];
+      const float ptyp = (float)(vconst[0] / (double)dot);
+      int e = 0;
+      const bool ok = ptyp > 0.f && isfinite(ptyp);
+      if (ok) { frexpf(ptyp, &e); e = 1 - e; }     // ptyp * 2^e in [1, 2)
+      exps[3] = e;
+      *kappa = (ok && center) ? ptyp : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_rowvec_kernel(float* __restrict__ x, int64_t n, int R, const float* __restrict__ v, const float* __restrict__ kappa) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] = fmaf(*kappa, v[i % R], x[i]);
+}
+
+// loss = sum V log(V+eps) - sum V - ln2 * 2^-v * sum v~ lg2(S+eps) + 2^-(aW+aH) * sum S~      (metrics.py:22)
+__global__ void tc_loss_final_kernel(const double* __restrict__ part, int nblk, const double* __restrict__ vconst,
+                                     const int* __restrict__ exps, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblk; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+  const double ln2 = 0.693147180559945309417;
+  *out = vconst[1] - vconst[0] - ln2 * exp2((double)-exps[0]) * a + exp2((double)-(exps[1] + exps[2])) * b;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -422,14 +627,20 @@ struct TcState {
   __half *V16 = nullptr, *Vt16 = nullptr, *W16 = nullptr, *H16 = nullptr;
   float* part = nullptr;
   int64_t part_floats = 0;
-  float* colsum = nullptr;       // [2][R]  0 = W, 1 = H
-  float* cs_scratch = nullptr;
-  int64_t cs_scratch_floats = 0;
-  unsigned int* absmax = nullptr;   // [2]
-  int* exps = nullptr;              // {v, aW, aH}
+  float* colsum = nullptr;          // [2][R]  0 = W, 1 = H
+  float* cs_part = nullptr;         // [<=1024][64]
+  unsigned int* absmax = nullptr;   // [2 factors][2 parities]
+  int* exps = nullptr;              // {v, aW, aH, p}
+  double* vpart = nullptr;          // per-block {sum V, sum V log V}
+  int64_t vblocks = 0;
+  double* vconst = nullptr;         // {sum V, sum V log(V+eps)}
+  double* loss_part = nullptr;      // [num_sms][2]
   CUtensorMap tmV, tmVt, tmW, tmH;
   Plan plan_w, plan_h;
+  uint32_t upd[2] = {0, 0};         // per-factor update counter (selects the absmax slot)
   bool dirty_w = true, dirty_h = true, has_target = false;
+  int center = 1;
+  float* kappa = nullptr;           // device scalar
 };
 
 bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
@@ -440,7 +651,8 @@ void tc_destroy(TcState* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part);
-  cudaFree(s->colsum); cudaFree(s->cs_scratch); cudaFree(s->absmax); cudaFree(s->exps);
+  cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->absmax); cudaFree(s->exps);
+  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa);
   delete s;
 }
 
@@ -449,6 +661,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   TcState* s = new TcState();
   s->device = device; s->N = N; s->C = C; s->R = R; s->split = split;
   s->KW = split ? 2 * kRp : kRp;
+  if (const char* e = getenv("NMFB200_CENTER")) s->center = atoi(e);
   s->ldc = round_up(C, 8);
   s->ldn = round_up(N, 8);
   cudaDeviceProp prop;
@@ -459,7 +672,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   s->plan_h = make_plan(N, C, s->num_sms);
   int64_t pw = (int64_t)s->plan_w.nchunks * C * kRp, ph = (int64_t)s->plan_h.nchunks * N * kRp;
   s->part_floats = pw > ph ? pw : ph;
-  s->cs_scratch_floats = colsum_scratch_floats(N > C ? N : C, (int)R, 1);
+  s->vblocks = ceil_div(C, 64) * ceil_div(N, 64);
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMalloc(&s->V16, (size_t)N * s->ldc * 2);
   if (e == cudaSuccess) e = cudaMalloc(&s->Vt16, (size_t)C * s->ldn * 2);
@@ -467,12 +680,20 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->H16, (size_t)N * s->KW * 2);
   if (e == cudaSuccess) e = cudaMalloc(&s->part, (size_t)s->part_floats * 4);
   if (e == cudaSuccess) e = cudaMalloc(&s->colsum, 2 * R * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&s->cs_scratch, s->cs_scratch_floats * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, 1024 * 64 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 4 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&s->vpart, (size_t)s->vblocks * 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->vconst, 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->num_sms * 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(s->kappa, 0, sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(s->W16, 0, (size_t)C * s->KW * 2);
   if (e == cudaSuccess) e = cudaMemset(s->H16, 0, (size_t)N * s->KW * 2);
   if (e == cudaSuccess) e = cudaMemset(s->exps, 0, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(s->absmax, 0, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(s->colsum, 0, 2 * R * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(s->vconst, 0, 2 * sizeof(double));
   if (e != cudaSuccess) {
     tc_destroy(s);
     set_error(std::string("tc_create cudaMalloc: ") + cudaGetErrorString(e));
@@ -489,15 +710,19 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
 }
 
 bool tc_supports_beta(const TcState*, double beta) { return beta == 1.0; }
-bool tc_supports_loss(const TcState*, double) { return false; }
+bool tc_supports_loss(const TcState*, double beta) { return beta == 1.0; }
 
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st) {
   set_vexp_kernel<<<1, 32, 0, st>>>(minmax_dev, s->exps);
   NMF_LAUNCH_CHECK();
   dim3 grid((unsigned)ceil_div(s->C, 64), (unsigned)ceil_div(s->N, 64));
-  v_to_f16_kernel<<<grid, 256, 0, st>>>(V, ldv, (int)s->N, (int)s->C, s->V16, s->ldc, s->Vt16, s->ldn, s->exps);
+  v_to_f16_kernel<<<grid, 256, 0, st>>>(V, ldv, (int)s->N, (int)s->C, s->V16, s->ldc, s->Vt16, s->ldn, s->exps,
+                                        s->vpart);
+  NMF_LAUNCH_CHECK();
+  reduce_vconst_kernel<<<1, 256, 0, st>>>(s->vpart, s->vblocks, s->vconst);
   NMF_LAUNCH_CHECK();
   s->has_target = true;
+  s->dirty_w = s->dirty_h = true;      // exps[3] depends on sum(V)
   return 0;
 }
 
@@ -508,39 +733,59 @@ void tc_mark_dirty(TcState* s, bool w, bool h) {
 
 namespace {
 
-// (re)build the fp16 operand copy + column sums of one factor; `have_absmax`: absmax[which] already holds max
-int refresh_factor(TcState* s, int which, const float* x, bool have_absmax, cudaStream_t st) {
+// ratio stage (apply != 0) or plain re-scan (apply == 0) of one factor, then rebuild its fp16 operand copy,
+// column sums and the exponents that depend on it: two launches.
+int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double gamma, double l1,
+                     double l2, cudaStream_t st) {
   const int64_t rows = which == 0 ? s->C : s->N;
-  const int64_t n = rows * s->R;
-  if (!have_absmax) {
-    NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax + which, 0, sizeof(unsigned int), st));
-    int64_t nb = ceil_div(n, 256 * 8);
-    if (nb > 1184) nb = 1184;
-    absmax_kernel<<<(unsigned)nb, 256, 0, st>>>(x, n, s->absmax + which);
-    NMF_LAUNCH_CHECK();
-  }
-  __half* out = which == 0 ? s->W16 : s->H16;
-  if (s->split)
-    factor_to_f16_kernel<true><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, rows, (int)s->R, out, s->KW,
-                                                                         s->absmax + which, s->exps, 1 + which);
-  else
-    factor_to_f16_kernel<false><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, rows, (int)s->R, out, s->KW,
-                                                                          s->absmax + which, s->exps, 1 + which);
+  int rpb = (int)round_up(ceil_div(rows, 1024), 4);
+  if (rpb < 64) rpb = 64;
+  const int blocks = (int)ceil_div(rows, rpb);
+  const uint32_t k = s->upd[which]++;
+  unsigned int* slot = s->absmax + which * 2 + (k & 1);
+  unsigned int* next = s->absmax + which * 2 + ((k + 1) & 1);
+  TcApplyArgs a{};
+  a.param = param; a.rows = rows; a.R = (int)s->R; a.rpb = rpb;
+  a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * kRp;
+  a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
+  a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
+  a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = s->kappa;
+  tc_apply_kernel<<<blocks, 256, 0, st>>>(a);
   NMF_LAUNCH_CHECK();
-  return factor_colsum(x, rows, (int)s->R, 1, s->cs_scratch, s->cs_scratch_floats, s->colsum + which * s->R, st);
+  __half* out = which == 0 ? s->W16 : s->H16;
+  const unsigned grid = (unsigned)ceil_div(rows * s->R, 256);
+  if (s->split)
+    tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, slot, next, s->exps, which,
+                                                 s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
+  else
+    tc_finish_kernel<false><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, slot, next, s->exps, which,
+                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
+  NMF_LAUNCH_CHECK();
+  return 0;
 }
 
 int ensure_synced(TcState* s, const float* W, const float* H, cudaStream_t st) {
   if (!s->has_target) { set_error("tensor-core path: set_target has not been called"); return 3; }
-  if (s->dirty_w) { int rc = refresh_factor(s, 0, W, false, st); if (rc) return rc; s->dirty_w = false; }
-  if (s->dirty_h) { int rc = refresh_factor(s, 1, H, false, st); if (rc) return rc; s->dirty_h = false; }
+  const bool both = s->dirty_w && s->dirty_h;
+  if (s->dirty_w) {
+    int rc = apply_and_finish(s, 0, const_cast<float*>(W), false, nullptr, 1, 0, 0, st);
+    if (rc) return rc;
+    s->dirty_w = false;
+  }
+  if (s->dirty_h) {
+    int rc = apply_and_finish(s, 1, const_cast<float*>(H), false, nullptr, 1, 0, 0, st);
+    if (rc) return rc;
+    s->dirty_h = false;
+  }
+  (void)both;   // the second refresh recomputes exps[3] with both column sums valid
   return 0;
 }
 
-template <int KW, int NST, bool SPLIT>
+template <int KW, int NF, int NG, int NV, bool SPLIT, bool LOSS>
 int launch_contract_t(TcState* s, int which, cudaStream_t st) {
-  using L = SmemLayout<KW, NST>;
-  auto kern = tc_contract_kernel<KW, NST, SPLIT>;
+  using L = SmemLayout<KW, NF, NG, NV>;
+  static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
+  auto kern = tc_contract_kernel<KW, NF, NG, NV, SPLIT, LOSS>;
   static bool attr_set = false;
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
   if (!attr_set) {
@@ -556,6 +801,8 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   p.exps = s->exps;
   p.ef = which == 0 ? 1 : 2;
   p.eg = which == 0 ? 2 : 1;
+  p.loss_part = s->loss_part;
+  p.kappa = s->kappa;
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
   if (which == 0)
@@ -563,28 +810,13 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   else
     kern<<<grid, kThreads, smem, st>>>(s->tmH, s->tmW, s->tmV, p);
   NMF_LAUNCH_CHECK();
-  return 0;
+  return grid;
 }
 
 int launch_contract(TcState* s, int which, cudaStream_t st) {
-  if (s->split) return launch_contract_t<2 * kRp, 2, true>(s, which, st);
-  return launch_contract_t<kRp, 3, false>(s, which, st);
-}
-
-int tc_apply(TcState* s, int which, float* param, double gamma, double l1, double l2, cudaStream_t st) {
-  const Plan& pl = which == 0 ? s->plan_w : s->plan_h;
-  const int64_t rows = which == 0 ? s->C : s->N;
-  NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax + which, 0, sizeof(unsigned int), st));
-  ApplyArgs a{};
-  a.param = param; a.numel = rows * s->R; a.R = (int)s->R; a.inner = 1; a.rowlen = s->R;
-  a.num = s->part; a.den = nullptr; a.nchunks = pl.nchunks; a.chunk_stride = rows * kRp; a.ldp = kRp;
-  a.kl_den = s->colsum + (which == 0 ? 1 : 0) * s->R;   // W update divides by colsum(H), H update by colsum(W)
-  a.out_scale = nullptr;
-  a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
-  a.absmax_bits = s->absmax + which;
-  int rc = apply_update(a, st);
-  if (rc) return rc;
-  return refresh_factor(s, which, param, true, st);
+  int g = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, true, false>(s, which, st)
+                   : launch_contract_t<kRp, 2, 4, 4, false, false>(s, which, st);
+  return g > 0 ? 0 : 2;
 }
 
 }  // namespace
@@ -596,7 +828,7 @@ int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma,
   if (rc) return rc;
   rc = launch_contract(s, 0, st);
   if (rc) return rc;
-  return tc_apply(s, 0, W, gamma, l1, l2, st);
+  return apply_and_finish(s, 0, W, true, &s->plan_w, gamma, l1, l2, st);
 }
 
 int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
@@ -606,7 +838,7 @@ int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma,
   if (rc) return rc;
   rc = launch_contract(s, 1, st);
   if (rc) return rc;
-  return tc_apply(s, 1, H, gamma, l1, l2, st);
+  return apply_and_finish(s, 1, H, true, &s->plan_h, gamma, l1, l2, st);
 }
 
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st) {
@@ -619,6 +851,9 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
   rc = reduce_chunks(s->part, s->plan_w.nchunks, s->C * kRp, s->C, (int)s->R, kRp, partial, st);
   if (rc) return rc;
   NMF_CUDA_CHECK(cudaMemcpyAsync(partial + CR, s->colsum + s->R, s->R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // the kernel accumulated sum_n (P - kappa) H: add kappa * colsum(H_local) back
+  add_rowvec_kernel<<<(unsigned)ceil_div(CR, 256), 256, 0, st>>>(partial, CR, (int)s->R, s->colsum + s->R, s->kappa);
+  NMF_LAUNCH_CHECK();
   return 0;
 }
 
@@ -629,9 +864,17 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
   return launch_contract(s, which, st);
 }
 
-int tc_loss(TcState*, const float*, const float*, double, double*, cudaStream_t) {
-  set_error("tensor-core loss kernel not available");
-  return 1;
+int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {
+  (void)beta;
+  int rc = ensure_synced(s, W, H, st);
+  if (rc) return rc;
+  // S = H W^T over the H-update decomposition (row blocks of H, tiles of W), no second GEMM
+  int grid = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, true, true>(s, 1, st)
+                      : launch_contract_t<kRp, 2, 4, 4, false, true>(s, 1, st);
+  if (grid <= 0) return 2;
+  tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
+  NMF_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace nmfb200

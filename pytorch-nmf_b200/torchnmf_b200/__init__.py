@@ -4,3 +4,4 @@ __version__ = "0.1.0"
 
 from . import constants, nmf  # noqa: F401
 from .nmf import NMF, NMFD, BaseComponent  # noqa: F401
+from .engine import release_workspaces  # noqa: F401

@@ -34,6 +34,20 @@ def _check_f32_cuda(t, name, device):
         raise ValueError(f"{name} must be contiguous")
 
 
+# Engine workspaces (the fp16 operand copies of V are the size of V) are kept across fit() calls of the same
+# shape instead of being cudaMalloc'ed / cudaFree'd every time.  release_workspaces() drops them.
+_WORKSPACES = {}
+_MAX_WORKSPACES = 2
+
+
+def release_workspaces():
+    """Free every cached engine workspace (device memory held between fit() calls)."""
+    lib = _capi.load()
+    for ctx in _WORKSPACES.values():
+        lib.nmfb200_destroy(ctx)
+    _WORKSPACES.clear()
+
+
 class _CudaEngine:
     kind = None
 
@@ -41,10 +55,26 @@ class _CudaEngine:
         self._lib = _capi.load()
         self._ctx = ctypes.c_void_p()
         self._loss = None
+        self._key = None
+
+    def _acquire(self, key, create):
+        """Take a cached context for `key` or create one with `create(ctx_ref)`."""
+        self._key = key
+        ctx = _WORKSPACES.pop(key, None)
+        if ctx is not None:
+            self._ctx = ctx
+            return
+        _capi.check(create(ctypes.byref(self._ctx)))
 
     def close(self):
         if self._ctx:
-            self._lib.nmfb200_destroy(self._ctx)
+            if self._key is not None:
+                while len(_WORKSPACES) >= _MAX_WORKSPACES:
+                    old = _WORKSPACES.pop(next(iter(_WORKSPACES)))
+                    self._lib.nmfb200_destroy(old)
+                _WORKSPACES[self._key] = self._ctx
+            else:
+                self._lib.nmfb200_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()
 
     def __del__(self):
@@ -82,8 +112,8 @@ class CudaNmfEngine(_CudaEngine):
         self.V, self.W, self.H = V, W, H
         self.N, self.C, self.R = N, C, R
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _capi.check(self._lib.nmfb200_nmf_create(ctypes.byref(self._ctx), dev_index, N, C, R,
-                                                 _capi.PRECISIONS[precision]))
+        self._acquire(("nmf", dev_index, N, C, R, precision),
+                      lambda ref: self._lib.nmfb200_nmf_create(ref, dev_index, N, C, R, _capi.PRECISIONS[precision]))
         self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         _capi.check(self._lib.nmfb200_nmf_set_target(self._ctx, _ptr(V), V.stride(0), _stream(self.device)))
         self.sync()
@@ -136,8 +166,9 @@ class CudaNmfdEngine(_CudaEngine):
         assert W.shape == (C, R, T) and H.shape == (B, R, L - T + 1)
         self.V, self.W, self.H = V, W, H
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _capi.check(self._lib.nmfb200_nmfd_create(ctypes.byref(self._ctx), dev_index, B, C, L, R, T,
-                                                  _capi.PRECISIONS[precision]))
+        self._acquire(("nmfd", dev_index, B, C, L, R, T, precision),
+                      lambda ref: self._lib.nmfb200_nmfd_create(ref, dev_index, B, C, L, R, T,
+                                                                _capi.PRECISIONS[precision]))
         self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         _capi.check(self._lib.nmfb200_nmfd_set_target(self._ctx, _ptr(V), _stream(self.device)))
 

@@ -250,3 +250,18 @@ def test_cfg2_200_iterations_match_reference_subsample():
     for got, want, mx, nm in ((W, Wg, float(z["w_absmax"]), "W"), (H, Hg, float(z["h_absmax"]), "H")):
         err = ((got - want).abs() / (want.abs() + TC_ATOL_REL * mx / TC_RTOL)).max().item()
         assert torch.allclose(got, want, rtol=TC_RTOL, atol=TC_ATOL_REL * mx), f"{nm} [{m.last_fit_precision}]: {err / TC_RTOL:.2f} x tol"
+
+
+@pytest.mark.parametrize("precision", ["f16", "f16_split"])
+def test_tc_loss_matches_oracle(precision):
+    torch.manual_seed(21)
+    N, C, R = 777, 515, 48
+    V = (torch.rand(N, C) * 3).bfloat16().float()
+    V[5, :7] = 0.0                              # exact zeros in the target are legal for beta = 1
+    W0 = torch.rand(C, R) + 0.01; H0 = torch.rand(N, R) + 0.01
+    from torchnmf_b200.engine import CudaNmfEngine
+    eng = CudaNmfEngine(V.cuda(), W0.cuda(), H0.cuda(), precision)
+    want = float(orc.beta_div(orc.nmf_reconstruct(H0, W0).double(), V.double(), 1))
+    got = eng.loss(1)
+    eng.close()
+    assert math.isclose(got, want, rel_tol=5e-5), (got, want)
