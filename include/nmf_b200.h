@@ -58,6 +58,10 @@ const char* nmfb200_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t     nmfb200_launch_count(void);
 
+/* Synchronises `stream` and reports whether any kernel of this library aborted an internal wait (a protocol
+ * bug or a wedged device): 0 = healthy, non-zero = the results since the last check are invalid. */
+int nmfb200_check_health(void* stream);
+
 /* ---- dense NMF ------------------------------------------------------------------------- */
 
 /* Allocate the engine workspace for an (N,C) target of rank R on CUDA device `device`.

@@ -99,6 +99,13 @@ int nmfb200_abi_version(void) { return NMFB200_ABI_VERSION; }
 const char* nmfb200_last_error(void) { return g_err.c_str(); }
 int64_t nmfb200_launch_count(void) { return g_launches.load(); }
 
+int nmfb200_check_health(void* stream) {
+  int rc = tc_check_wait_abort((cudaStream_t)stream);
+  if (rc > 0) return fail(NMFB200_ERR_STATE, "a kernel aborted an internal barrier wait; results are invalid");
+  if (rc < 0) return fail(NMFB200_ERR_CUDA, std::string("stream synchronize: ") + cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
 int nmfb200_nmf_create(nmfb200_ctx** out, int device, int64_t N, int64_t C, int64_t R, int precision) {
   if (!out) return fail(NMFB200_ERR_INVALID, "out is null");
   *out = nullptr;

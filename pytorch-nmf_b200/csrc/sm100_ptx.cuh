@@ -39,14 +39,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU box.
+// Bounded wait: on a protocol bug (no progress for ~1 s) the first waiter records (block, thread, barrier, parity)
+// in g_wait_abort and every wait in the grid then falls through, so the kernel terminates instead of hanging
+// the GPU box; the host checks the record after the launch (tc_nmf.cu: check_wait_abort).
+__device__ unsigned int g_wait_abort[8];
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-      printf("nmf_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+    if (*reinterpret_cast<volatile unsigned int*>(&g_wait_abort[0]) != 0u) return;
+    if (clock64() - t0 > 2000000000LL) {
+      if (atomicCAS(&g_wait_abort[0], 0u, 1u) == 0u) {
+        g_wait_abort[1] = blockIdx.x; g_wait_abort[2] = threadIdx.x; g_wait_abort[3] = bar; g_wait_abort[4] = parity;
+        __threadfence();
+      }
+      return;
     }
   }
 }
@@ -60,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, 
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+
+// fire-and-forget prefetch of one box into L2 (no shared memory, no mbarrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y)
+               : "memory");
 }
 
 // ---- tcgen05 ------------------------------------------------------------------------------------
@@ -138,6 +152,23 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
          | (0u << 7) | (0u << 10)        // a_format = b_format = F16
          | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// descriptor split into a loop-invariant high word and a low word that only carries the start address, so the
+// issue loop advances operands with one 32-bit add (saddr < 256 KB: (saddr >> 4) never carries into the LBO field)
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- small math helpers ----------------------------------------------------------------------------

@@ -49,7 +49,14 @@ struct TcKernelParams {
   int ef, eg;                 // which of exps[] belong to F and G
   double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
   const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
+  int pf_dist;                // L2 prefetch distance of the V stream in tiles (0 = off)
+  long long* trace;           // tuning aid: per-tile event timestamps of CTA 0 ([tile][12]), or nullptr
 };
+
+#define TC_TRACE(tile, k)                                                        \
+  do {                                                                         \
+    if (p.trace && blockIdx.x == 0 && (tile) < 256) p.trace[(tile) * 12 + (k)] = clock64(); \
+  } while (0)
 
 // shared memory: NF F blocks | NG G-tile ring | NV V-tile ring | mbarriers | tmem ptr | loss slots
 template <int KW, int NF, int NG, int NV>
@@ -67,7 +74,7 @@ struct SmemLayout {
   static constexpr int kTotal = kLossSlots + 16 * 8;
 };
 
-template <int KW, int NF, int NG, int NV, bool SPLIT, bool LOSS>
+template <int KW, int NF, int NG, int NV, int AHEAD, bool SPLIT, bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
@@ -112,7 +119,31 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
 
   if (warp == 0) {
     // =========================== TMA producer: V tiles (the HBM stream) =================================
+    // HBM latency under load (~3 us) times the per-SM share of the bandwidth is more than the shared-memory ring
+    // can hold in flight, so the stream is staged through L2: tile t + kPfDist is prefetched into L2 (no smem,
+    // no barrier) while tile t is copied L2 -> smem into the ring.
     if (lane == 0) {
+      const int kPfDist = p.pf_dist;
+      int pf_item = blockIdx.x, pf_j = 0, pf_te = 0, pf_rb = 0;
+      bool pf_live = pf_item < total_items;
+      auto pf_load_item = [&]() {
+        pf_rb = pf_item % p.row_blocks;
+        const int chunk = pf_item / p.row_blocks;
+        pf_j = chunk * p.tiles_per_chunk;
+        pf_te = min(p.tiles, pf_j + p.tiles_per_chunk);
+      };
+      auto pf_issue_and_advance = [&]() {
+        if (!pf_live) return;
+        ptx::tma_prefetch_l2_2d(&tmV, pf_j * kTileN, pf_rb * kTileM);
+        ptx::tma_prefetch_l2_2d(&tmV, pf_j * kTileN + 64, pf_rb * kTileM);
+        if (++pf_j >= pf_te) {
+          pf_item += gridDim.x;
+          pf_live = pf_item < total_items;
+          if (pf_live) pf_load_item();
+        }
+      };
+      if (pf_live) pf_load_item();
+      for (int k = 0; k < kPfDist; ++k) pf_issue_and_advance();
       uint32_t t = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int rb = item % p.row_blocks, chunk = item / p.row_blocks;
@@ -120,7 +151,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const int te = min(p.tiles, tb + p.tiles_per_chunk);
         for (int j = tb; j < te; ++j, ++t) {
           const uint32_t s = t % NV, ph = (t / NV) & 1;
+          if (kPfDist > 0) pf_issue_and_advance();
           ptx::mbar_wait(BAR(B_VEMPTY + s), ph ^ 1);
+          TC_TRACE(t, 7);
           ptx::mbar_expect_tx(BAR(B_VFULL + s), L::kVBytes);
           for (int vb = 0; vb < 2; ++vb)
             ptx::tma_load_2d(&tmV, BAR(B_VFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * kTileN + vb * 64,
@@ -144,6 +177,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         for (int j = tb; j < te; ++j, ++t) {
           const uint32_t s = t % NG, ph = (t / NG) & 1;
           ptx::mbar_wait(BAR(B_GEMPTY + s), ph ^ 1);
+          TC_TRACE(t, 8);
           ptx::mbar_expect_tx(BAR(B_GFULL + s), L::kGBytes);
           for (int kb = 0; kb < KW / 64; ++kb)
             ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (kTileN * 128), kb * 64, j * kTileN);
@@ -152,80 +186,105 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform values (ring cursors, descriptors live in uniform
+    // registers); only the tcgen05.mma / commit instructions are issued by one elected lane.
+    {
       constexpr uint32_t idescS = ptx::idesc_f16(kTileM, kTileN, 0, 0);
       constexpr uint32_t idescO = ptx::idesc_f16(kTileM, KW, 0, 1);
-      uint32_t it = 0, t = 0;
+      constexpr uint32_t descHi = ptx::smem_desc_hi_sw128(1024);
       // S = sum over terms (F part, G part): fast: (0,0); split: (hi,hi), (lo,hi), (hi,lo)
       constexpr int kTerms = SPLIT ? 3 : 1;
-      const int termF[3] = {0, 1, 0}, termG[3] = {0, 0, 1};
+      constexpr int termF[3] = {0, 1, 0}, termG[3] = {0, 0, 1};
+      uint32_t it = 0;
+      uint32_t f_s = 0, f_ph = 0;                 // F block ring
+      uint32_t sg = 0, sg_ph = 0, ss = 0;         // next S issue: G stage/phase, S stage
+      uint32_t og = 0, os = 0, os_ph = 0;         // next O issue: G stage, S/P stage + p_full phase
+      uint32_t ts = 0, to = 0;                    // tile counters (trace only)
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int chunk = item / p.row_blocks;
         const int tb = chunk * p.tiles_per_chunk;
         const int te = min(p.tiles, tb + p.tiles_per_chunk);
         const int n = te - tb;
-        const uint32_t fb = it % NF;
-        ptx::mbar_wait(BAR(B_FFULL + fb), (it / NF) & 1);
+        if (lane == 0) ptx::mbar_wait(BAR(B_FFULL + f_s), f_ph);
+        __syncwarp();      // one poller; the warp is converged again before any elect.sync / tcgen05 issue
         ptx::tc_fence_after();
-        const uint32_t fbase = sF + fb * L::kFBytes;
+        const uint32_t fbase = sF + f_s * L::kFBytes;
+        const uint32_t f_bar = BAR(B_FEMPTY + f_s);
+        if (++f_s == NF) { f_s = 0; f_ph ^= 1; }
 
-        // S stage of tile tt is free once O(tt - kSStages) consumed its P: that MMA was issued earlier by this
-        // thread, and the tensor pipe executes in issue order.
-        auto issue_S = [&](uint32_t tt) {
-          const uint32_t s = tt % NG, st = tt % kSStages;
-          ptx::mbar_wait(BAR(B_GFULL + s), (tt / NG) & 1);
-          ptx::tc_fence_after();
-          const uint32_t gbase = sG + s * L::kGBytes;
-          uint32_t acc = 0;
-#pragma unroll
-          for (int term = 0; term < kTerms; ++term) {
-            const uint32_t fa = fbase + termF[term] * (kTileM * 128);
-            const uint32_t ga = gbase + termG[term] * (kTileN * 128);
-#pragma unroll
-            for (int ks = 0; ks < kRp / 16; ++ks) {
-              const uint64_t ad = ptx::smem_desc_sw128(fa + ks * 32, 16, 1024);
-              const uint64_t bd = ptx::smem_desc_sw128(ga + ks * 32, 16, 1024);
-              ptx::mma_ss(tmem + kColS + st * 128, ad, bd, idescS, acc);
-              acc = 1;
-            }
+        // S stage of a tile is free once the O-MMA of the tile kSStages earlier consumed its P: that MMA was
+        // issued earlier by this warp, and the tensor pipe executes in issue order.
+        auto issue_S = [&]() {
+          if (lane == 0) {
+            TC_TRACE(ts, 0);
+            ptx::mbar_wait(BAR(B_GFULL + sg), sg_ph);
+            TC_TRACE(ts, 1);
           }
-          ptx::mma_commit(BAR(B_SFULL + st));
-        };
-        auto issue_O = [&](uint32_t tt, bool first, bool last) {
-          const uint32_t s = tt % NG, st = tt % kSStages;
-          ptx::mbar_wait(BAR(B_PFULL + st), (tt / kSStages) & 1);
-          if (first) ptx::mbar_wait(BAR(B_OEMPTY), (it & 1) ^ 1);
+          __syncwarp();
           ptx::tc_fence_after();
-          const uint32_t gbase = sG + s * L::kGBytes;
+          const uint32_t gbase = sG + sg * L::kGBytes;
+          const uint32_t dS = tmem + kColS + ss * 128;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kTileN / 16; ++ks) {
+            for (int term = 0; term < kTerms; ++term) {
+              const uint32_t alo = ptx::smem_desc_lo(fbase + termF[term] * (kTileM * 128), 16);
+              const uint32_t blo = ptx::smem_desc_lo(gbase + termG[term] * (kTileN * 128), 16);
+#pragma unroll
+              for (int ks = 0; ks < kRp / 16; ++ks)
+                ptx::mma_ss(dS, ptx::make_desc(alo + 2 * ks, descHi), ptx::make_desc(blo + 2 * ks, descHi), idescS,
+                            (term | ks) ? 1u : 0u);
+            }
+            ptx::mma_commit(BAR(B_SFULL + ss));
+          }
+          __syncwarp();
+          if (++sg == NG) { sg = 0; sg_ph ^= 1; }
+          if (++ss == kSStages) ss = 0;
+          ++ts;
+        };
+        auto issue_O = [&](bool first, bool last) {
+          if (lane == 0) {
+            TC_TRACE(to, 5);
+            ptx::mbar_wait(BAR(B_PFULL + os), os_ph);
+            if (first && !LOSS) ptx::mbar_wait(BAR(B_OEMPTY), (it & 1) ^ 1);   // (no epilogue in LOSS mode)
+            TC_TRACE(to, 6);
+          }
+          __syncwarp();
+          ptx::tc_fence_after();
+          if (LOSS) {
+            if (ptx::elect_one()) ptx::mbar_arrive(BAR(B_GEMPTY + og));    // ratio warpgroup consumed S
+          } else {
             // B = G tile as [K = 16 c-rows][N = KW] MN-major: 8-row groups 1024 B apart, 64-wide column blocks
             // (hi | lo) one tile-block (16 KB) apart
-            const uint64_t bd = ptx::smem_desc_sw128(gbase + ks * 2048, kTileN * 128, 1024);
-            ptx::mma_ts(tmem + kColO, tmem + kColS + st * 128 + ks * 8, bd, idescO, (first && ks == 0) ? 0u : 1u);
+            const uint32_t blo = ptx::smem_desc_lo(sG + og * L::kGBytes, kTileN * 128);
+            const uint32_t aP = tmem + kColS + os * 128;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < kTileN / 16; ++ks)
+                ptx::mma_ts(tmem + kColO, aP + ks * 8, ptx::make_desc(blo + ks * 128, descHi), idescO,
+                            (first && ks == 0) ? 0u : 1u);
+              ptx::mma_commit(BAR(B_GEMPTY + og));
+              if (last) ptx::mma_commit(BAR(B_OFULL));
+            }
           }
-          ptx::mma_commit(BAR(B_GEMPTY + s));
-          if (last) ptx::mma_commit(BAR(B_OFULL));
+          __syncwarp();
+          if (++og == NG) og = 0;
+          if (++os == kSStages) { os = 0; os_ph ^= 1; }
+          ++to;
         };
 
-        // software pipeline: S runs (kSStages - 1) tiles ahead of O
-        constexpr int kAhead = kSStages - 1;
-        for (int j = 0; j < kAhead && j < n; ++j) issue_S(t + j);
-        if (n <= kAhead) ptx::mma_commit(BAR(B_FEMPTY + fb));
+        // software pipeline: S runs AHEAD tiles ahead of O (needs AHEAD < kSStages and NG >= AHEAD + 2 to hide
+        // the G-tile reload behind the tensor pipe)
+        constexpr int kAhead = AHEAD;
+        static_assert(AHEAD >= 1 && AHEAD < kSStages, "S lookahead");
+        for (int j = 0; j < kAhead && j < n; ++j) issue_S();
+        if (n <= kAhead && ptx::elect_one()) ptx::mma_commit(f_bar);
         for (int j = 0; j < n; ++j) {
           if (j + kAhead < n) {
-            issue_S(t + j + kAhead);
-            if (j + kAhead == n - 1) ptx::mma_commit(BAR(B_FEMPTY + fb));   // last S of the item issued
+            issue_S();
+            if (j + kAhead == n - 1 && ptx::elect_one()) ptx::mma_commit(f_bar);   // last S of the item issued
           }
-          if (LOSS) {
-            const uint32_t tt = t + j;
-            ptx::mbar_wait(BAR(B_PFULL + tt % kSStages), (tt / kSStages) & 1);   // ratio warpgroup consumed S(tt)
-            ptx::mbar_arrive(BAR(B_GEMPTY + tt % NG));
-          } else {
-            issue_O(t + j, j == 0, j == n - 1);
-          }
+          issue_O(j == 0, j == n - 1);
         }
-        t += n;
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -256,8 +315,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const uint32_t tt = t + j;
         if ((int)(tt & 1) != g) continue;
         const uint32_t s = tt % NV, st = tt % kSStages;
+        if (q == 0 && lane == 0) TC_TRACE(tt, 2);
         ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);              // V tile landed (TMA -> this thread)
+        if (q == 0 && lane == 0) TC_TRACE(tt, 3);
         ptx::mbar_wait(BAR(B_SFULL + st), (tt / kSStages) & 1);       // S tile complete
+        if (q == 0 && lane == 0) TC_TRACE(tt, 4);
         ptx::tc_fence_after();
         const uint32_t vrow = sV + s * L::kVBytes + row * 128;
 #pragma unroll
@@ -305,6 +367,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(B_PFULL + st));
         ptx::mbar_arrive(BAR(B_VEMPTY + s));
+        if (q == 0 && lane == 0) TC_TRACE(tt, 9);
       }
       t += n;
     }
@@ -640,6 +703,10 @@ struct TcState {
   uint32_t upd[2] = {0, 0};         // per-factor update counter (selects the absmax slot)
   bool dirty_w = true, dirty_h = true, has_target = false;
   int center = 1;
+  int pf_dist = 0;
+  int variant = 0;                  // pipeline configuration (NMFB200_TC_VARIANT, tuning aid)
+  long long* trace = nullptr;       // NMFB200_TC_TRACE=<file>: event timestamps of CTA 0 (tuning aid)
+  const char* trace_path = nullptr;
   float* kappa = nullptr;           // device scalar
 };
 
@@ -652,7 +719,7 @@ void tc_destroy(TcState* s) {
   cudaSetDevice(s->device);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->absmax); cudaFree(s->exps);
-  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa);
+  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa); cudaFree(s->trace);
   delete s;
 }
 
@@ -662,6 +729,12 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   s->device = device; s->N = N; s->C = C; s->R = R; s->split = split;
   s->KW = split ? 2 * kRp : kRp;
   if (const char* e = getenv("NMFB200_CENTER")) s->center = atoi(e);
+  if (const char* e = getenv("NMFB200_TC_VARIANT")) s->variant = atoi(e);
+  if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
+  if (const char* e = getenv("NMFB200_TC_TRACE")) {
+    s->trace_path = e;
+    cudaMalloc(&s->trace, 256 * 12 * sizeof(long long));
+  }
   s->ldc = round_up(C, 8);
   s->ldn = round_up(N, 8);
   cudaDeviceProp prop;
@@ -781,11 +854,11 @@ int ensure_synced(TcState* s, const float* W, const float* H, cudaStream_t st) {
   return 0;
 }
 
-template <int KW, int NF, int NG, int NV, bool SPLIT, bool LOSS>
+template <int KW, int NF, int NG, int NV, int AHEAD, bool SPLIT, bool LOSS>
 int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   using L = SmemLayout<KW, NF, NG, NV>;
   static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
-  auto kern = tc_contract_kernel<KW, NF, NG, NV, SPLIT, LOSS>;
+  auto kern = tc_contract_kernel<KW, NF, NG, NV, AHEAD, SPLIT, LOSS>;
   static bool attr_set = false;
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
   if (!attr_set) {
@@ -803,6 +876,9 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   p.eg = which == 0 ? 2 : 1;
   p.loss_part = s->loss_part;
   p.kappa = s->kappa;
+  p.trace = s->trace;
+  p.pf_dist = s->pf_dist;
+  if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 12 * sizeof(long long), st);
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
   if (which == 0)
@@ -814,8 +890,20 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
 }
 
 int launch_contract(TcState* s, int which, cudaStream_t st) {
-  int g = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, true, false>(s, which, st)
-                   : launch_contract_t<kRp, 2, 4, 4, false, false>(s, which, st);
+  // <KW, F blocks, G ring, V ring, S lookahead>: 224 KB of shared memory either way.  Tuning notes (profiles/README.md):
+  // the V ring must hold >= 3 tiles in flight to cover HBM latency, the G ring >= lookahead + 2.
+  int g;
+  if (s->split) {
+    switch (s->variant) {
+      case 1: g = launch_contract_t<2 * kRp, 1, 4, 2, 2, true, false>(s, which, st); break;
+      default: g = launch_contract_t<2 * kRp, 1, 3, 3, 1, true, false>(s, which, st); break;
+    }
+  } else {
+    switch (s->variant) {
+      case 1: g = launch_contract_t<kRp, 1, 5, 4, 2, false, false>(s, which, st); break;
+      default: g = launch_contract_t<kRp, 2, 4, 4, 2, false, false>(s, which, st); break;
+    }
+  }
   return g > 0 ? 0 : 2;
 }
 
@@ -857,11 +945,42 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
   return 0;
 }
 
+// debugging aid: report (and clear) a recorded mbarrier wait abort; synchronises the stream
+int tc_check_wait_abort(cudaStream_t st) {
+  unsigned int h[8] = {0};
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  cudaMemcpyFromSymbol(h, ptx::g_wait_abort, sizeof(h));
+  if (h[0]) {
+    fprintf(stderr, "nmf_b200: mbarrier wait aborted: block %u thread %u (warp %u) bar_addr %u parity %u\n", h[1], h[2], h[2] / 32,
+            h[3], h[4]);
+    unsigned int z[8] = {0};
+    cudaMemcpyToSymbol(ptx::g_wait_abort, z, sizeof(z));
+    return 1;
+  }
+  return 0;
+}
+
 int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st) {
   (void)beta;
   int rc = ensure_synced(s, W, H, st);
   if (rc) return rc;
-  return launch_contract(s, which, st);
+  rc = launch_contract(s, which, st);
+  if (rc == 0 && getenv("NMFB200_TC_CHECK")) {
+    if (tc_check_wait_abort(st) > 0) { set_error("mbarrier wait aborted (protocol bug)"); return 2; }
+  }
+  if (rc == 0 && s->trace) {
+    std::vector<long long> h(256 * 12);
+    cudaMemcpyAsync(h.data(), s->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (FILE* f = fopen(s->trace_path, "w")) {
+      for (int t = 0; t < 256; ++t) {
+        for (int k = 0; k < 12; ++k) fprintf(f, "%lld ", h[t * 12 + k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+  return rc;
 }
 
 int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {
@@ -869,8 +988,8 @@ int tc_loss(TcState* s, const float* W, const float* H, double beta, double* los
   int rc = ensure_synced(s, W, H, st);
   if (rc) return rc;
   // S = H W^T over the H-update decomposition (row blocks of H, tiles of W), no second GEMM
-  int grid = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, true, true>(s, 1, st)
-                      : launch_contract_t<kRp, 2, 4, 4, false, true>(s, 1, st);
+  int grid = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, 1, true, true>(s, 1, st)
+                      : launch_contract_t<kRp, 2, 4, 4, 2, false, true>(s, 1, st);
   if (grid <= 0) return 2;
   tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
   NMF_LAUNCH_CHECK();

@@ -22,6 +22,7 @@ SIGNATURES = {
     "nmfb200_abi_version": (_int, []),
     "nmfb200_last_error": (_c.c_char_p, []),
     "nmfb200_launch_count": (_i64, []),
+    "nmfb200_check_health": (_int, [_vp]),
     "nmfb200_nmf_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _int]),
     "nmfb200_destroy": (None, [_vp]),
     "nmfb200_precision": (_int, [_vp]),

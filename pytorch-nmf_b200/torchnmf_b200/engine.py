@@ -94,7 +94,13 @@ class _CudaEngine:
         return vmin.value, vmax.value
 
     def loss(self, beta):
-        return float(self.loss_tensor(beta).item())
+        val = float(self.loss_tensor(beta).item())
+        self.check_health()
+        return val
+
+    def check_health(self):
+        """Raise if a kernel of the library aborted an internal wait since the last check (synchronises)."""
+        _capi.check(self._lib.nmfb200_check_health(_stream(self.device)))
 
 
 class CudaNmfEngine(_CudaEngine):
@@ -240,4 +246,10 @@ class ShardedEngine:
     def loss(self, beta):
         t = self.local.loss_tensor(beta).clone()
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
-        return float(t.item())
+        val = float(t.item())
+        self.check_health()
+        return val
+
+    def check_health(self):
+        if hasattr(self.local, "check_health"):
+            self.local.check_health()

@@ -194,6 +194,8 @@ class BaseComponent(torch.nn.Module):
                         if (previous_loss - loss) / loss_init < tol:                       # nmf.py:405
                             break
                         previous_loss = loss
+            if hasattr(eng, "check_health"):
+                eng.check_health()
             if staged:
                 W.data.copy_(Wd)
                 H.data.copy_(Hd)
