@@ -551,6 +551,64 @@ tc_apply_kernel(TcApplyArgs a) {
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
 }
 
+// Vectorised variant for R % 4 == 0: one thread owns 4 consecutive rank lanes (float4) of a row; a 256-thread block
+// covers 256 / (R/4) rows per pass.  Same outputs as tc_apply_kernel.
+__global__ void __launch_bounds__(256)
+tc_apply_vec4_kernel(TcApplyArgs a) {
+  __shared__ float4 sh[256];
+  const int lanes = a.R >> 2;                    // threads per row
+  const int rows_per_pass = 256 / lanes;
+  const int rl = threadIdx.x / lanes, q = threadIdx.x - rl * lanes;      // row slot, rank quad
+  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
+  const int64_t row1 = min(a.rows, row0 + a.rpb);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  float mx = 0.f;
+  if (rl < rows_per_pass) {
+    float4 kd = make_float4(1.f, 1.f, 1.f, 1.f);
+    float kap = 0.f;
+    if (a.apply) { kd = *reinterpret_cast<const float4*>(a.kl_den + 4 * q); kap = *a.kappa; }
+    for (int64_t row = row0 + rl; row < row1; row += rows_per_pass) {
+      float4* pp = reinterpret_cast<float4*>(a.param + row * a.R) + q;
+      float4 v = *pp;
+      if (a.apply) {
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * kRp) + q);
+          num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
+        }
+        float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float n = fmaf(kap, dd[i], nn[i]);                  // the kernel accumulated sum (P - kappa) G
+          const float neg = fmaxf(n, 0.f) + kEps;                   // nmf.py:78
+          float pos = dd[i];                                        // nmf.py:368-369 / :381-382
+          if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
+          if (a.l2 > 0.f) pos = fmaf(a.l2, vv[i], pos);             // nmf.py:87-88
+          float mult = neg / pos;                                   // nmf.py:89
+          if (a.gamma != 1.0f) mult = powf(mult, a.gamma);          // nmf.py:90-91
+          vv[i] *= mult;                                            // nmf.py:92
+        }
+        v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        *pp = v;
+      }
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+      mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+  }
+  sh[threadIdx.x] = cs;
+  __syncthreads();
+  if (threadIdx.x < lanes) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rows_per_pass; ++k) {
+      const float4 u = sh[k * lanes + threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    *(reinterpret_cast<float4*>(a.cs_part + (int64_t)blockIdx.x * 64) + threadIdx.x) = t;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
+}
+
 // fp32 factor (rows x R) -> fp16 operand copy (rows x KW): [hi(0..Rp) | lo(Rp..2Rp)] scaled by 2^a, a from the
 // max found by tc_apply_kernel; pad columns stay zero (buffer zero-initialised once).  Block 0 additionally
 // finishes the column sums, publishes exps[1 + which] = a, and re-derives kappa = sum(V) / sum(W H^T) =
@@ -564,14 +622,35 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
                  float* __restrict__ kappa, int center) {
   const int a = pow2_exp_for(__uint_as_float(*absmax));
   const float sc = exp2f((float)a);
-  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (idx < rows * R) {
-    const int64_t row = idx / R;
-    const int r = (int)(idx - row * R);
-    const float xs = x[idx] * sc;
-    const __half hi = __float2half_rn(xs);
-    out[row * KW + r] = hi;
-    if (SPLIT) out[row * KW + kRp + r] = __float2half_rn(xs - __half2float(hi));
+  if ((R & 7) == 0) {
+    // 8 consecutive rank lanes per thread: two float4 loads, one 16-byte store per half
+    const int per_row = R >> 3;
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g < rows * per_row) {
+      const int64_t row = g / per_row;
+      const int r8 = (int)(g - row * per_row) * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(x + row * R + r8);
+      const float4 a1 = *reinterpret_cast<const float4*>(x + row * R + r8 + 4);
+      const float xv[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc, a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
+      __half2 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = __floats2half2_rn(xv[2 * i], xv[2 * i + 1]);
+        const float2 hf = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(xv[2 * i] - hf.x, xv[2 * i + 1] - hf.y);
+      }
+      *reinterpret_cast<uint4*>(out + row * KW + r8) = *reinterpret_cast<const uint4*>(hi);
+      if (SPLIT) *reinterpret_cast<uint4*>(out + row * KW + kRp + r8) = *reinterpret_cast<const uint4*>(lo);
+    }
+  } else {
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < rows * R; idx += (int64_t)gridDim.x * 256) {
+      const int64_t row = idx / R;
+      const int r = (int)(idx - row * R);
+      const float xs = x[idx] * sc;
+      const __half hi = __float2half_rn(xs);
+      out[row * KW + r] = hi;
+      if (SPLIT) out[row * KW + kRp + r] = __float2half_rn(xs - __half2float(hi));
+    }
   }
   if (blockIdx.x == 0) {
     // fixed-order final column sums: 4 thread groups x 64 rank lanes, 4 independent accumulators each
@@ -823,10 +902,13 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = s->kappa;
-  tc_apply_kernel<<<blocks, 256, 0, st>>>(a);
+  if ((s->R & 3) == 0)
+    tc_apply_vec4_kernel<<<blocks, 256, 0, st>>>(a);
+  else
+    tc_apply_kernel<<<blocks, 256, 0, st>>>(a);
   NMF_LAUNCH_CHECK();
   __half* out = which == 0 ? s->W16 : s->H16;
-  const unsigned grid = (unsigned)ceil_div(rows * s->R, 256);
+  const unsigned grid = (unsigned)ceil_div((s->R & 7) == 0 ? rows * (s->R >> 3) : rows * s->R, 256);
   if (s->split)
     tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, slot, next, s->exps, which,
                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);

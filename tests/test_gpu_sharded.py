@@ -1,0 +1,60 @@
+"""2-GPU NCCL test of the row-sharded fit (skipped unless >= 2 CUDA devices): sharded == single-GPU within rtol."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _inputs():
+    torch.manual_seed(0)
+    N, C, R = 2048, 768, 64
+    V = torch.rand(N, C).bfloat16().float()
+    torch.manual_seed(1)
+    return V, torch.randn(C, R).abs(), torch.randn(N, R).abs()
+
+
+def _worker(rank, world, port, precision, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "pytorch-nmf_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from torchnmf_b200 import NMF
+    V, W0, H0 = _inputs()
+    bounds = [0, 1152, V.shape[0]]          # uneven shards
+    lo, hi = bounds[rank], bounds[rank + 1]
+    m = NMF(W=W0, H=H0[lo:hi]).cuda()
+    n = m.fit(V[lo:hi].cuda(), 1, 1e-5, 40, precision=precision, group=dist.group.WORLD)
+    torch.save({"W": m.W.data.cpu(), "H": m.H.data.cpu(), "n": n}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier(); dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("precision", ["f32", "f16_split"])
+def test_two_gpu_sharded_fit_matches_single(tmp_path, precision):
+    from torchnmf_b200 import NMF
+    mp.spawn(_worker, args=(2, _free_port(), precision, str(tmp_path)), nprocs=2, join=True)
+    V, W0, H0 = _inputs()
+    ref = NMF(W=W0, H=H0).cuda()
+    n_ref = ref.fit(V.cuda(), 1, 1e-5, 40, precision=precision)
+    parts = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
+    assert parts[0]["n"] == parts[1]["n"] == n_ref
+    assert torch.equal(parts[0]["W"], parts[1]["W"])                     # replicas stay bit-identical
+    H = torch.cat([p["H"] for p in parts])
+    rtol = 1e-4 if precision == "f32" else 5e-4
+    assert torch.allclose(parts[0]["W"], ref.W.data.cpu(), rtol=rtol, atol=1e-6)
+    assert torch.allclose(H, ref.H.data.cpu(), rtol=rtol, atol=1e-6)
