@@ -31,13 +31,21 @@ namespace nmfb200 {
 
 namespace {
 
-constexpr int kRp = 64;              // padded rank handled by this kernel
-constexpr int kTileM = 128, kTileN = 128;
+constexpr int kTileM = 128;          // rows of the row factor per work item (= TMEM lanes)
 constexpr int kThreads = 512;
-constexpr int kSStages = 3;           // S/P accumulator stages in TMEM
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0;        // S/P stages: columns [128 i, 128 i + 128)
-constexpr uint32_t kColO = 128 * kSStages;   // O accumulator: [384, 384 + KW)
+constexpr uint32_t kColS = 0;        // S/P stages: columns [TN i, TN i + TN); O accumulator follows at NS * TN
+
+// Compile-time configuration of the fused kernel.
+//   RP    padded rank (64 or 128);  SPLIT  hi|lo fp16 factors (KW = 2 RP operand columns)
+//   TN    tile width in columns of V (64 or 128): narrower tiles = deeper rings in the same shared memory
+//   NF / NG / NV  F blocks, G-tile ring, V-tile ring;  NS  S/P accumulator stages in TMEM;  AHEAD  S lookahead
+template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int AHEAD_>
+struct Cfg {
+  static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, AHEAD = AHEAD_;
+  static constexpr bool SPLIT = SPLIT_;
+  static constexpr int KW = RP_ * (SPLIT_ ? 2 : 1);
+};
 
 struct TcKernelParams {
   int Mr, Nc;                 // valid rows of F / rows of G (= columns of Vm)
@@ -59,27 +67,32 @@ struct TcKernelParams {
   } while (0)
 
 // shared memory: NF F blocks | NG G-tile ring | NV V-tile ring | mbarriers | tmem ptr | loss slots
-template <int KW, int NF, int NG, int NV>
+template <int KW, int TN, int NF, int NG, int NV, int NS>
 struct SmemLayout {
   static constexpr int kFBytes = kTileM * KW * 2;
-  static constexpr int kGBytes = kTileN * KW * 2;
-  static constexpr int kVBytes = kTileM * kTileN * 2;
+  static constexpr int kGBytes = TN * KW * 2;
+  static constexpr int kVBytes = kTileM * TN * 2;
   static constexpr int kF = 0;
   static constexpr int kG = kF + NF * kFBytes;
   static constexpr int kV = kG + NG * kGBytes;
   static constexpr int kBar = kV + NV * kVBytes;
-  static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 2 * kSStages + 2;
+  static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 2 * NS + 2;
   static constexpr int kTmemPtr = kBar + 8 * kNumBars;
   static constexpr int kLossSlots = kTmemPtr + 16;
   static constexpr int kTotal = kLossSlots + 16 * 8;
 };
 
-template <int KW, int NF, int NG, int NV, int AHEAD, bool SPLIT, bool LOSS>
+template <class C, bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
-  using L = SmemLayout<KW, NF, NG, NV>;
-  static_assert(kSStages * 128 + KW <= (int)kTmemCols, "TMEM budget");
+  constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS, AHEAD = C::AHEAD;
+  constexpr bool SPLIT = C::SPLIT;
+  constexpr uint32_t kColO = NS * TN;
+  using L = SmemLayout<KW, TN, NF, NG, NV, NS>;
+  static_assert(NS * TN + KW <= (int)kTmemCols, "TMEM budget");
+  static_assert(TN == 64 || TN == 128, "tile width");
+  static_assert(RP == 64 || RP == 128, "padded rank");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw32 = ptx::smem_u32(smem_raw);
   const uint32_t sbase = (raw32 + 1023u) & ~1023u;
@@ -88,8 +101,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   const uint32_t bar0 = sbase + L::kBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_FFULL = 0, B_FEMPTY = NF, B_GFULL = 2 * NF, B_GEMPTY = B_GFULL + NG, B_VFULL = B_GEMPTY + NG,
-                B_VEMPTY = B_VFULL + NV, B_SFULL = B_VEMPTY + NV, B_PFULL = B_SFULL + kSStages,
-                B_OFULL = B_PFULL + kSStages, B_OEMPTY = B_OFULL + 1;
+                B_VEMPTY = B_VFULL + NV, B_SFULL = B_VEMPTY + NV, B_PFULL = B_SFULL + NS,
+                B_OFULL = B_PFULL + NS, B_OEMPTY = B_OFULL + 1;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + L::kTmemPtr);
   double* loss_slots = reinterpret_cast<double*>(smem_al + L::kLossSlots);      // [8 ratio warps][2]
 
@@ -100,7 +113,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     for (int i = 0; i < NF; ++i) { ptx::mbar_init(BAR(B_FFULL + i), 1); ptx::mbar_init(BAR(B_FEMPTY + i), 1); }
     for (int i = 0; i < NG; ++i) { ptx::mbar_init(BAR(B_GFULL + i), 1); ptx::mbar_init(BAR(B_GEMPTY + i), 1); }
     for (int i = 0; i < NV; ++i) { ptx::mbar_init(BAR(B_VFULL + i), 1); ptx::mbar_init(BAR(B_VEMPTY + i), 128); }
-    for (int i = 0; i < kSStages; ++i) { ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128); }
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128); }
     ptx::mbar_init(BAR(B_OFULL), 1);
     ptx::mbar_init(BAR(B_OEMPTY), 128);
     ptx::fence_barrier_init();
@@ -134,8 +147,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       };
       auto pf_issue_and_advance = [&]() {
         if (!pf_live) return;
-        ptx::tma_prefetch_l2_2d(&tmV, pf_j * kTileN, pf_rb * kTileM);
-        ptx::tma_prefetch_l2_2d(&tmV, pf_j * kTileN + 64, pf_rb * kTileM);
+        for (int vb = 0; vb < TN / 64; ++vb) ptx::tma_prefetch_l2_2d(&tmV, pf_j * TN + vb * 64, pf_rb * kTileM);
         if (++pf_j >= pf_te) {
           pf_item += gridDim.x;
           pf_live = pf_item < total_items;
@@ -155,8 +167,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           ptx::mbar_wait(BAR(B_VEMPTY + s), ph ^ 1);
           TC_TRACE(t, 7);
           ptx::mbar_expect_tx(BAR(B_VFULL + s), L::kVBytes);
-          for (int vb = 0; vb < 2; ++vb)
-            ptx::tma_load_2d(&tmV, BAR(B_VFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * kTileN + vb * 64,
+          for (int vb = 0; vb < TN / 64; ++vb)
+            ptx::tma_load_2d(&tmV, BAR(B_VFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * TN + vb * 64,
                              rb * kTileM);
         }
       }
@@ -180,7 +192,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           TC_TRACE(t, 8);
           ptx::mbar_expect_tx(BAR(B_GFULL + s), L::kGBytes);
           for (int kb = 0; kb < KW / 64; ++kb)
-            ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (kTileN * 128), kb * 64, j * kTileN);
+            ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (TN * 128), kb * 64, j * TN);
         }
       }
     }
@@ -189,7 +201,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     // The whole warp runs this loop with warp-uniform values (ring cursors, descriptors live in uniform
     // registers); only the tcgen05.mma / commit instructions are issued by one elected lane.
     {
-      constexpr uint32_t idescS = ptx::idesc_f16(kTileM, kTileN, 0, 0);
+      constexpr uint32_t idescS = ptx::idesc_f16(kTileM, TN, 0, 0);
       constexpr uint32_t idescO = ptx::idesc_f16(kTileM, KW, 0, 1);
       constexpr uint32_t descHi = ptx::smem_desc_hi_sw128(1024);
       // S = sum over terms (F part, G part): fast: (0,0); split: (hi,hi), (lo,hi), (hi,lo)
@@ -212,7 +224,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const uint32_t f_bar = BAR(B_FEMPTY + f_s);
         if (++f_s == NF) { f_s = 0; f_ph ^= 1; }
 
-        // S stage of a tile is free once the O-MMA of the tile kSStages earlier consumed its P: that MMA was
+        // S stage of a tile is free once the O-MMA of the tile NS earlier consumed its P: that MMA was
         // issued earlier by this warp, and the tensor pipe executes in issue order.
         auto issue_S = [&]() {
           if (lane == 0) {
@@ -223,22 +235,24 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           __syncwarp();
           ptx::tc_fence_after();
           const uint32_t gbase = sG + sg * L::kGBytes;
-          const uint32_t dS = tmem + kColS + ss * 128;
+          const uint32_t dS = tmem + kColS + ss * TN;
           if (ptx::elect_one()) {
 #pragma unroll
             for (int term = 0; term < kTerms; ++term) {
-              const uint32_t alo = ptx::smem_desc_lo(fbase + termF[term] * (kTileM * 128), 16);
-              const uint32_t blo = ptx::smem_desc_lo(gbase + termG[term] * (kTileN * 128), 16);
+              // operand halves (hi / lo) are RP/64 sub-blocks of 64 columns each; a k-step is 32 B inside a sub-block
 #pragma unroll
-              for (int ks = 0; ks < kRp / 16; ++ks)
-                ptx::mma_ss(dS, ptx::make_desc(alo + 2 * ks, descHi), ptx::make_desc(blo + 2 * ks, descHi), idescS,
-                            (term | ks) ? 1u : 0u);
+              for (int ks = 0; ks < RP / 16; ++ks) {
+                const uint32_t alo = ptx::smem_desc_lo(fbase + (termF[term] * (RP / 64) + ks / 4) * (kTileM * 128), 16);
+                const uint32_t blo = ptx::smem_desc_lo(gbase + (termG[term] * (RP / 64) + ks / 4) * (TN * 128), 16);
+                ptx::mma_ss(dS, ptx::make_desc(alo + 2 * (ks % 4), descHi), ptx::make_desc(blo + 2 * (ks % 4), descHi),
+                            idescS, (term | ks) ? 1u : 0u);
+              }
             }
             ptx::mma_commit(BAR(B_SFULL + ss));
           }
           __syncwarp();
           if (++sg == NG) { sg = 0; sg_ph ^= 1; }
-          if (++ss == kSStages) ss = 0;
+          if (++ss == NS) ss = 0;
           ++ts;
         };
         auto issue_O = [&](bool first, bool last) {
@@ -254,12 +268,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             if (ptx::elect_one()) ptx::mbar_arrive(BAR(B_GEMPTY + og));    // ratio warpgroup consumed S
           } else {
             // B = G tile as [K = 16 c-rows][N = KW] MN-major: 8-row groups 1024 B apart, 64-wide column blocks
-            // (hi | lo) one tile-block (16 KB) apart
-            const uint32_t blo = ptx::smem_desc_lo(sG + og * L::kGBytes, kTileN * 128);
-            const uint32_t aP = tmem + kColS + os * 128;
+            // (hi | lo, RP/64 blocks each) one sub-block (TN x 128 B) apart
+            const uint32_t blo = ptx::smem_desc_lo(sG + og * L::kGBytes, TN * 128);
+            const uint32_t aP = tmem + kColS + os * TN;
             if (ptx::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < kTileN / 16; ++ks)
+              for (int ks = 0; ks < TN / 16; ++ks)
                 ptx::mma_ts(tmem + kColO, aP + ks * 8, ptx::make_desc(blo + ks * 128, descHi), idescO,
                             (first && ks == 0) ? 0u : 1u);
               ptx::mma_commit(BAR(B_GEMPTY + og));
@@ -268,14 +282,14 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           }
           __syncwarp();
           if (++og == NG) og = 0;
-          if (++os == kSStages) { os = 0; os_ph ^= 1; }
+          if (++os == NS) { os = 0; os_ph ^= 1; }
           ++to;
         };
 
-        // software pipeline: S runs AHEAD tiles ahead of O (needs AHEAD < kSStages and NG >= AHEAD + 2 to hide
+        // software pipeline: S runs AHEAD tiles ahead of O (needs AHEAD < NS and NG >= AHEAD + 2 to hide
         // the G-tile reload behind the tensor pipe)
         constexpr int kAhead = AHEAD;
-        static_assert(AHEAD >= 1 && AHEAD < kSStages, "S lookahead");
+        static_assert(AHEAD >= 1 && AHEAD < NS, "S lookahead");
         for (int j = 0; j < kAhead && j < n; ++j) issue_S();
         if (n <= kAhead && ptx::elect_one()) ptx::mma_commit(f_bar);
         for (int j = 0; j < n; ++j) {
@@ -314,18 +328,18 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       for (int j = 0; j < n; ++j) {
         const uint32_t tt = t + j;
         if ((int)(tt & 1) != g) continue;
-        const uint32_t s = tt % NV, st = tt % kSStages;
+        const uint32_t s = tt % NV, st = tt % NS;
         if (q == 0 && lane == 0) TC_TRACE(tt, 2);
         ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);              // V tile landed (TMA -> this thread)
         if (q == 0 && lane == 0) TC_TRACE(tt, 3);
-        ptx::mbar_wait(BAR(B_SFULL + st), (tt / kSStages) & 1);       // S tile complete
+        ptx::mbar_wait(BAR(B_SFULL + st), (tt / NS) & 1);       // S tile complete
         if (q == 0 && lane == 0) TC_TRACE(tt, 4);
         ptx::tc_fence_after();
         const uint32_t vrow = sV + s * L::kVBytes + row * 128;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < TN / 32; ++c4) {
           uint32_t sreg[32];
-          ptx::tmem_ld32(tmem + lane_addr + kColS + st * 128 + c4 * 32, sreg);
+          ptx::tmem_ld32(tmem + lane_addr + kColS + st * TN + c4 * 32, sreg);
           uint4 vv[4];
           const uint32_t vsub = vrow + (c4 >> 1) * (kTileM * 128);
 #pragma unroll
@@ -360,7 +374,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
               const float p1 = fmaf(vf.y, ptx::rcp_approx(x1), negpc);
               preg[i] = ptx::pack_f16x2_sat(p0, p1);
             }
-            ptx::tmem_st16(tmem + lane_addr + kColS + st * 128 + c4 * 16, preg);
+            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, preg);
           }
         }
         if (!LOSS) ptx::tc_wait_st();
@@ -392,13 +406,13 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       const int64_t grow = (int64_t)rb * kTileM + row;
       float* dst = p.part + (int64_t)chunk * p.chunk_stride + grow * p.ldp;
 #pragma unroll
-      for (int c = 0; c < kRp / 32; ++c) {
+      for (int c = 0; c < RP / 32; ++c) {
         uint32_t hi[32];
         ptx::tmem_ld32(tmem + lane_addr + kColO + c * 32, hi);
         float o[32];
         if (SPLIT) {
           uint32_t lo[32];
-          ptx::tmem_ld32(tmem + lane_addr + kColO + kRp + c * 32, lo);
+          ptx::tmem_ld32(tmem + lane_addr + kColO + RP + c * 32, lo);
           ptx::tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * oscale;
@@ -506,9 +520,9 @@ reduce_vconst_kernel(const double* __restrict__ vpart, int64_t nblk, double* __r
 // (-> power-of-two scale of the fp16 operand copy).
 struct TcApplyArgs {
   float* param; int64_t rows; int R; int rpb;
-  const float* num; int nchunks; int64_t chunk_stride;     // pitch kRp
+  const float* num; int nchunks; int64_t chunk_stride; int Rp;     // partial row pitch = padded rank
   const float* kl_den; float gamma, l1, l2;
-  float* cs_part;            // [gridDim.x][64]
+  float* cs_part;            // [gridDim.x][128]
   const float* kappa;        // the kernel accumulated sum (P - kappa) G: add kappa * colsum(G) back
   unsigned int* absmax;      // slot to atomicMax into (pre-zeroed)
   int apply;                 // 0: only emit column sums / max of the current values (dirty-factor resync)
@@ -516,20 +530,20 @@ struct TcApplyArgs {
 
 __global__ void __launch_bounds__(256)
 tc_apply_kernel(TcApplyArgs a) {
-  __shared__ float sh[4][64];
-  const int r = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  __shared__ float sh[2][128];
+  const int r = threadIdx.x & 127, rg = threadIdx.x >> 7;
   const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
   const int64_t row1 = min(a.rows, row0 + a.rpb);
   float cs = 0.f, mx = 0.f;
   if (r < a.R) {
     const float klden = a.apply ? a.kl_den[r] : 1.f;
     const float kap = a.apply ? *a.kappa : 0.f;
-    for (int64_t row = row0 + rg; row < row1; row += 4) {
+    for (int64_t row = row0 + rg; row < row1; row += 2) {
       const int64_t idx = row * a.R + r;
       float v = a.param[idx];
       if (a.apply) {
         float num = 0.f;
-        for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * kRp + r];
+        for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * a.Rp + r];
         num = fmaf(kap, klden, num);                            // the kernel accumulated sum (P - kappa) G
         const float neg = fmaxf(num, 0.f) + kEps;              // nmf.py:78
         float pos = klden;                                      // nmf.py:368-369 / :381-382
@@ -546,7 +560,7 @@ tc_apply_kernel(TcApplyArgs a) {
   }
   sh[rg][r] = cs;
   __syncthreads();
-  if (threadIdx.x < 64) a.cs_part[(int64_t)blockIdx.x * 64 + r] = (sh[0][r] + sh[1][r]) + (sh[2][r] + sh[3][r]);
+  if (threadIdx.x < 128) a.cs_part[(int64_t)blockIdx.x * 128 + r] = sh[0][r] + sh[1][r];
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
 }
@@ -573,7 +587,7 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
       if (a.apply) {
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ch = 0; ch < a.nchunks; ++ch) {
-          const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * kRp) + q);
+          const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * a.Rp) + q);
           num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
         }
         float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
@@ -603,7 +617,7 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
       const float4 u = sh[k * lanes + threadIdx.x];
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
-    *(reinterpret_cast<float4*>(a.cs_part + (int64_t)blockIdx.x * 64) + threadIdx.x) = t;
+    *(reinterpret_cast<float4*>(a.cs_part + (int64_t)blockIdx.x * 128) + threadIdx.x) = t;
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
@@ -615,7 +629,7 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
 // sum(V) / <colsum W, colsum H> (the typical P = V / (WH)) and the ratio-tile exponent exps[3] with kappa 2^p in [1, 2).
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __restrict__ out, int KW,
+tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __restrict__ out, int KW, int Rp,
                  const unsigned int* __restrict__ absmax, unsigned int* __restrict__ absmax_next,
                  int* __restrict__ exps, int which, const float* __restrict__ cs_part, int cs_blocks,
                  float* __restrict__ colsum /* [2][R] */, const double* __restrict__ vconst,
@@ -640,7 +654,7 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
         lo[i] = __floats2half2_rn(xv[2 * i] - hf.x, xv[2 * i + 1] - hf.y);
       }
       *reinterpret_cast<uint4*>(out + row * KW + r8) = *reinterpret_cast<const uint4*>(hi);
-      if (SPLIT) *reinterpret_cast<uint4*>(out + row * KW + kRp + r8) = *reinterpret_cast<const uint4*>(lo);
+      if (SPLIT) *reinterpret_cast<uint4*>(out + row * KW + Rp + r8) = *reinterpret_cast<const uint4*>(lo);
     }
   } else {
     for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < rows * R; idx += (int64_t)gridDim.x * 256) {
@@ -649,27 +663,27 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
       const float xs = x[idx] * sc;
       const __half hi = __float2half_rn(xs);
       out[row * KW + r] = hi;
-      if (SPLIT) out[row * KW + kRp + r] = __float2half_rn(xs - __half2float(hi));
+      if (SPLIT) out[row * KW + Rp + r] = __float2half_rn(xs - __half2float(hi));
     }
   }
   if (blockIdx.x == 0) {
-    // fixed-order final column sums: 4 thread groups x 64 rank lanes, 4 independent accumulators each
-    __shared__ float part4[4][64];
-    __shared__ float prod[64];
-    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+    // fixed-order final column sums: 2 thread groups x 128 rank lanes, 4 independent accumulators each
+    __shared__ float part2[2][128];
+    __shared__ float prod[128];
+    const int r = threadIdx.x & 127, g = threadIdx.x >> 7;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int b = g;
-    for (; b + 12 < cs_blocks; b += 16) {
-      a0 += cs_part[(int64_t)b * 64 + r];
-      a1 += cs_part[(int64_t)(b + 4) * 64 + r];
-      a2 += cs_part[(int64_t)(b + 8) * 64 + r];
-      a3 += cs_part[(int64_t)(b + 12) * 64 + r];
+    for (; b + 6 < cs_blocks; b += 8) {
+      a0 += cs_part[(int64_t)b * 128 + r];
+      a1 += cs_part[(int64_t)(b + 2) * 128 + r];
+      a2 += cs_part[(int64_t)(b + 4) * 128 + r];
+      a3 += cs_part[(int64_t)(b + 6) * 128 + r];
     }
-    for (; b < cs_blocks; b += 4) a0 += cs_part[(int64_t)b * 64 + r];
-    part4[g][r] = (a0 + a1) + (a2 + a3);
+    for (; b < cs_blocks; b += 2) a0 += cs_part[(int64_t)b * 128 + r];
+    part2[g][r] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (threadIdx.x < 64) {
-      const float mine = (part4[0][r] + part4[1][r]) + (part4[2][r] + part4[3][r]);
+    if (threadIdx.x < 128) {
+      const float mine = part2[0][r] + part2[1][r];
       if (r < R) colsum[which * R + r] = mine;
       prod[r] = r < R ? mine * colsum[(1 - which) * R + r] : 0.f;
     }
@@ -678,7 +692,7 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
       exps[1 + which] = a;
       *absmax_next = 0u;
       float dot = 0.f;
-      for (int k = 0; k < 64; ++k) dot += prod[k];
+      for (int k = 0; k < 128; ++k) dot += prod[k];
       const float ptyp = (float)(vconst[0] / (double)dot);
       int e = 0;
       const bool ok = ptyp > 0.f && isfinite(ptyp);
@@ -719,13 +733,13 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2-D fp16 row-major tensor (rows x cols, row pitch ld elements), box 64 cols x 128 rows, SWIZZLE_128B
-int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+// 2-D fp16 row-major tensor (rows x cols, row pitch ld elements), box 64 cols x box_rows rows, SWIZZLE_128B
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 2; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -736,15 +750,15 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 
 struct Plan { int row_blocks, tiles, nchunks, tpc; };
 
-Plan make_plan(int64_t Mr, int64_t Nc, int num_sms) {
+Plan make_plan(int64_t Mr, int64_t Nc, int num_sms, int TN) {
   Plan pl;
   pl.row_blocks = (int)ceil_div(Mr, kTileM);
-  pl.tiles = (int)ceil_div(Nc, kTileN);
+  pl.tiles = (int)ceil_div(Nc, TN);
   int best = 1;
   double best_eff = -1.0;
   for (int nch = 1; nch <= pl.tiles && nch <= 64; ++nch) {
     int tpc = (int)ceil_div(pl.tiles, nch);
-    if (tpc < 4 && nch > 1) break;
+    if (tpc * TN < 512 && nch > 1) break;
     int real = (int)ceil_div(pl.tiles, tpc);
     if (real != nch) continue;
     int64_t items = (int64_t)pl.row_blocks * nch;
@@ -764,6 +778,8 @@ struct TcState {
   int device = 0, num_sms = 148;
   int64_t N = 0, C = 0, R = 0;
   bool split = true;
+  int Rp = 64;                      // padded rank: 64 or 128
+  int TN = 128;                     // tile width of the contraction kernel for this (Rp, split)
   int KW = 128;
   int64_t ldc = 0, ldn = 0;
   __half *V16 = nullptr, *Vt16 = nullptr, *W16 = nullptr, *H16 = nullptr;
@@ -777,7 +793,9 @@ struct TcState {
   int64_t vblocks = 0;
   double* vconst = nullptr;         // {sum V, sum V log(V+eps)}
   double* loss_part = nullptr;      // [num_sms][2]
-  CUtensorMap tmV, tmVt, tmW, tmH;
+  CUtensorMap tmV, tmVt;            // V16 / Vt16, box 64 x 128
+  CUtensorMap tmWf, tmHf;           // factors as the row factor F: box 64 x 128
+  CUtensorMap tmWg, tmHg;           // factors as the column factor G: box 64 x TN
   Plan plan_w, plan_h;
   uint32_t upd[2] = {0, 0};         // per-factor update counter (selects the absmax slot)
   bool dirty_w = true, dirty_h = true, has_target = false;
@@ -790,7 +808,7 @@ struct TcState {
 };
 
 bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
-  return R >= 1 && R <= kRp && N >= 1 && C >= 1 && N < (1ll << 31) && C < (1ll << 31);
+  return R >= 1 && R <= 128 && N >= 1 && C >= 1 && N < (1ll << 31) && C < (1ll << 31);
 }
 
 void tc_destroy(TcState* s) {
@@ -806,9 +824,11 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   *out = nullptr;
   TcState* s = new TcState();
   s->device = device; s->N = N; s->C = C; s->R = R; s->split = split;
-  s->KW = split ? 2 * kRp : kRp;
-  if (const char* e = getenv("NMFB200_CENTER")) s->center = atoi(e);
   if (const char* e = getenv("NMFB200_TC_VARIANT")) s->variant = atoi(e);
+  s->Rp = R <= 64 ? 64 : 128;
+  s->KW = split ? 2 * s->Rp : s->Rp;
+  s->TN = (split && s->Rp == 128) ? 64 : 128;   // 64-column tiles only where 128 do not fit (measured slower: MMA issue rate)
+  if (const char* e = getenv("NMFB200_CENTER")) s->center = atoi(e);
   if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
   if (const char* e = getenv("NMFB200_TC_TRACE")) {
     s->trace_path = e;
@@ -820,9 +840,10 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   NMF_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   s->num_sms = prop.multiProcessorCount;
   if (prop.major != 10) { delete s; set_error("the tensor-core path needs an sm_100 device"); return 1; }
-  s->plan_w = make_plan(C, N, s->num_sms);
-  s->plan_h = make_plan(N, C, s->num_sms);
-  int64_t pw = (int64_t)s->plan_w.nchunks * C * kRp, ph = (int64_t)s->plan_h.nchunks * N * kRp;
+  if (s->variant == 1 && split && s->Rp == 64) s->TN = 64;
+  s->plan_w = make_plan(C, N, s->num_sms, s->TN);
+  s->plan_h = make_plan(N, C, s->num_sms, s->TN);
+  int64_t pw = (int64_t)s->plan_w.nchunks * C * s->Rp, ph = (int64_t)s->plan_h.nchunks * N * s->Rp;
   s->part_floats = pw > ph ? pw : ph;
   s->vblocks = ceil_div(C, 64) * ceil_div(N, 64);
   cudaError_t e = cudaSuccess;
@@ -832,7 +853,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->H16, (size_t)N * s->KW * 2);
   if (e == cudaSuccess) e = cudaMalloc(&s->part, (size_t)s->part_floats * 4);
   if (e == cudaSuccess) e = cudaMalloc(&s->colsum, 2 * R * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, 1024 * 64 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, 1024 * 128 * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 4 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->vpart, (size_t)s->vblocks * 2 * sizeof(double));
@@ -852,10 +873,12 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
     return 2;
   }
   int rc = 0;
-  rc |= make_tmap(&s->tmV, s->V16, N, C, s->ldc);
-  rc |= make_tmap(&s->tmVt, s->Vt16, C, N, s->ldn);
-  rc |= make_tmap(&s->tmW, s->W16, C, s->KW, s->KW);
-  rc |= make_tmap(&s->tmH, s->H16, N, s->KW, s->KW);
+  rc |= make_tmap(&s->tmV, s->V16, N, C, s->ldc, kTileM);
+  rc |= make_tmap(&s->tmVt, s->Vt16, C, N, s->ldn, kTileM);
+  rc |= make_tmap(&s->tmWf, s->W16, C, s->KW, s->KW, kTileM);
+  rc |= make_tmap(&s->tmHf, s->H16, N, s->KW, s->KW, kTileM);
+  rc |= make_tmap(&s->tmWg, s->W16, C, s->KW, s->KW, s->TN);
+  rc |= make_tmap(&s->tmHg, s->H16, N, s->KW, s->KW, s->TN);
   if (rc) { tc_destroy(s); return 2; }
   *out = s;
   return 0;
@@ -898,7 +921,7 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   unsigned int* next = s->absmax + which * 2 + ((k + 1) & 1);
   TcApplyArgs a{};
   a.param = param; a.rows = rows; a.R = (int)s->R; a.rpb = rpb;
-  a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * kRp;
+  a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * s->Rp; a.Rp = s->Rp;
   a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = s->kappa;
@@ -910,10 +933,10 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   __half* out = which == 0 ? s->W16 : s->H16;
   const unsigned grid = (unsigned)ceil_div((s->R & 7) == 0 ? rows * (s->R >> 3) : rows * s->R, 256);
   if (s->split)
-    tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, slot, next, s->exps, which,
+    tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
   else
-    tc_finish_kernel<false><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, slot, next, s->exps, which,
+    tc_finish_kernel<false><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
                                                   s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
   NMF_LAUNCH_CHECK();
   return 0;
@@ -936,23 +959,24 @@ int ensure_synced(TcState* s, const float* W, const float* H, cudaStream_t st) {
   return 0;
 }
 
-template <int KW, int NF, int NG, int NV, int AHEAD, bool SPLIT, bool LOSS>
+template <class C, bool LOSS>
 int launch_contract_t(TcState* s, int which, cudaStream_t st) {
-  using L = SmemLayout<KW, NF, NG, NV>;
+  using L = SmemLayout<C::KW, C::TN, C::NF, C::NG, C::NV, C::NS>;
   static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
-  auto kern = tc_contract_kernel<KW, NF, NG, NV, AHEAD, SPLIT, LOSS>;
+  auto kern = tc_contract_kernel<C, LOSS>;
   static bool attr_set = false;
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
   if (!attr_set) {
     NMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  if (C::TN != s->TN || C::RP != s->Rp) { set_error("internal: kernel configuration does not match the plan"); return -1; }
   TcKernelParams p{};
   const Plan& pl = which == 0 ? s->plan_w : s->plan_h;
   p.Mr = (int)(which == 0 ? s->C : s->N);
   p.Nc = (int)(which == 0 ? s->N : s->C);
   p.row_blocks = pl.row_blocks; p.tiles = pl.tiles; p.nchunks = pl.nchunks; p.tiles_per_chunk = pl.tpc;
-  p.part = s->part; p.chunk_stride = (int64_t)p.Mr * kRp; p.ldp = kRp;
+  p.part = s->part; p.chunk_stride = (int64_t)p.Mr * s->Rp; p.ldp = s->Rp;
   p.exps = s->exps;
   p.ef = which == 0 ? 1 : 2;
   p.eg = which == 0 ? 2 : 1;
@@ -964,29 +988,35 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
   if (which == 0)
-    kern<<<grid, kThreads, smem, st>>>(s->tmW, s->tmH, s->tmVt, p);
+    kern<<<grid, kThreads, smem, st>>>(s->tmWf, s->tmHg, s->tmVt, p);
   else
-    kern<<<grid, kThreads, smem, st>>>(s->tmH, s->tmW, s->tmV, p);
+    kern<<<grid, kThreads, smem, st>>>(s->tmHf, s->tmWg, s->tmV, p);
   NMF_LAUNCH_CHECK();
   return grid;
 }
 
-int launch_contract(TcState* s, int which, cudaStream_t st) {
-  // <KW, F blocks, G ring, V ring, S lookahead>: 224 KB of shared memory either way.  Tuning notes (profiles/README.md):
-  // the V ring must hold >= 3 tiles in flight to cover HBM latency, the G ring >= lookahead + 2.
-  int g;
-  if (s->split) {
-    switch (s->variant) {
-      case 1: g = launch_contract_t<2 * kRp, 1, 4, 2, 2, true, false>(s, which, st); break;
-      default: g = launch_contract_t<2 * kRp, 1, 3, 3, 1, true, false>(s, which, st); break;
-    }
-  } else {
-    switch (s->variant) {
-      case 1: g = launch_contract_t<kRp, 1, 5, 4, 2, false, false>(s, which, st); break;
-      default: g = launch_contract_t<kRp, 2, 4, 4, 2, false, false>(s, which, st); break;
-    }
+// Kernel configurations <RP, SPLIT, TN, NF, NG, NV, NS, AHEAD> (224 KB of shared memory each).  Tuning notes in
+// profiles/README.md: the V ring must keep >= 3 tiles (>= 64 KB) in flight to cover HBM latency, the G ring needs
+// >= AHEAD + 2 stages, and AHEAD = 2 lets both ratio warpgroups work concurrently.
+using CfgFast64 = Cfg<64, false, 128, 2, 4, 4, 3, 2>;      // F 2x16 | G 4x16 | V 4x32 KB ; TMEM 3x128 + 64
+using CfgSplit64 = Cfg<64, true, 128, 1, 3, 3, 3, 1>;       // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
+using CfgSplit64N = Cfg<64, true, 64, 1, 6, 6, 4, 2>;       // (variant 1) 64-column tiles, deeper rings: slower, MMA-issue bound
+using CfgFast128 = Cfg<128, false, 128, 1, 3, 3, 3, 1>;     // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
+using CfgSplit128 = Cfg<128, true, 64, 1, 3, 4, 4, 1>;      // F 64 | G 3x32 | V 4x16 KB     ; TMEM 4x64 + 256
+
+template <bool LOSS>
+int launch_contract_any(TcState* s, int which, cudaStream_t st) {
+  if (s->Rp == 64) {
+    if (!s->split) return launch_contract_t<CfgFast64, LOSS>(s, which, st);
+    if (s->TN == 64) return launch_contract_t<CfgSplit64N, LOSS>(s, which, st);
+    return launch_contract_t<CfgSplit64, LOSS>(s, which, st);
   }
-  return g > 0 ? 0 : 2;
+  if (!s->split) return launch_contract_t<CfgFast128, LOSS>(s, which, st);
+  return launch_contract_t<CfgSplit128, LOSS>(s, which, st);
+}
+
+int launch_contract(TcState* s, int which, cudaStream_t st) {
+  return launch_contract_any<false>(s, which, st) > 0 ? 0 : 2;
 }
 
 }  // namespace
@@ -1018,7 +1048,7 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
   rc = launch_contract(s, 0, st);
   if (rc) return rc;
   const int64_t CR = s->C * s->R;
-  rc = reduce_chunks(s->part, s->plan_w.nchunks, s->C * kRp, s->C, (int)s->R, kRp, partial, st);
+  rc = reduce_chunks(s->part, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp, partial, st);
   if (rc) return rc;
   NMF_CUDA_CHECK(cudaMemcpyAsync(partial + CR, s->colsum + s->R, s->R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // the kernel accumulated sum_n (P - kappa) H: add kappa * colsum(H_local) back
@@ -1070,8 +1100,7 @@ int tc_loss(TcState* s, const float* W, const float* H, double beta, double* los
   int rc = ensure_synced(s, W, H, st);
   if (rc) return rc;
   // S = H W^T over the H-update decomposition (row blocks of H, tiles of W), no second GEMM
-  int grid = s->split ? launch_contract_t<2 * kRp, 1, 3, 3, 1, true, true>(s, 1, st)
-                      : launch_contract_t<kRp, 2, 4, 4, 2, false, true>(s, 1, st);
+  int grid = launch_contract_any<true>(s, 1, st);
   if (grid <= 0) return 2;
   tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
   NMF_LAUNCH_CHECK();

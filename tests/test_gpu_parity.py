@@ -173,7 +173,8 @@ def test_tc_path_matches_reference_golden(name, precision):
         assert ok, f"{name} {precision} {nm}: scaled err {err:.3e}"
 
 
-@pytest.mark.parametrize("shape", [(128, 128, 64), (1000, 700, 20), (130, 2049, 33), (257, 129, 1), (4096, 1024, 64)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (1000, 700, 20), (130, 2049, 33), (257, 129, 1), (4096, 1024, 64),
+                                   (512, 384, 128), (300, 260, 100), (1100, 777, 65)])
 @pytest.mark.parametrize("precision", ["f16", "f16_split"])
 def test_tc_single_updates_match_oracle(shape, precision):
     N, C, R = shape

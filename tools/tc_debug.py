@@ -40,7 +40,7 @@ def run(N, C, R, prec):
 
 if __name__ == "__main__":
     prec = sys.argv[1] if len(sys.argv) > 1 else "f16"
-    shapes = [(128, 128, 64), (384, 256, 64), (300, 200, 40), (2048, 1024, 64)]
+    shapes = [(128, 128, 64), (384, 256, 64), (300, 200, 40), (2048, 1024, 64), (512, 384, 128), (300, 260, 100)]
     for s in shapes:
         run(*s, prec)
     print("done", prec)
