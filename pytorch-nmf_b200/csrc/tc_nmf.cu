@@ -405,6 +405,34 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       ptx::tc_fence_after();
       const int64_t grow = (int64_t)rb * kTileM + row;
       float* dst = p.part + (int64_t)chunk * p.chunk_stride + grow * p.ldp;
+      if (RP == 64) {
+        // whole O row (64 values) into registers, hand the accumulator back to the MMA warp, then store
+        float o[64];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hi[32];
+          ptx::tmem_ld32(tmem + lane_addr + kColO + c * 32, hi);
+          if (SPLIT) {
+            uint32_t lo[32];
+            ptx::tmem_ld32(tmem + lane_addr + kColO + RP + c * 32, lo);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] = (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * oscale;
+          } else {
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(hi[i]) * oscale;
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(BAR(B_OEMPTY));
+        if (grow < p.Mr) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < RP / 32; ++c) {
         uint32_t hi[32];
@@ -633,7 +661,7 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
                  const unsigned int* __restrict__ absmax, unsigned int* __restrict__ absmax_next,
                  int* __restrict__ exps, int which, const float* __restrict__ cs_part, int cs_blocks,
                  float* __restrict__ colsum /* [2][R] */, const double* __restrict__ vconst,
-                 float* __restrict__ kappa, int center) {
+                 float* __restrict__ kappa, int center, float* __restrict__ cs_super, unsigned int* __restrict__ ticket) {
   const int a = pow2_exp_for(__uint_as_float(*absmax));
   const float sc = exp2f((float)a);
   if ((R & 7) == 0) {
@@ -666,39 +694,60 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
       if (SPLIT) out[row * KW + Rp + r] = __float2half_rn(xs - __half2float(hi));
     }
   }
-  if (blockIdx.x == 0) {
-    // fixed-order final column sums: 2 thread groups x 128 rank lanes, 4 independent accumulators each
-    __shared__ float part2[2][128];
-    __shared__ float prod[128];
-    const int r = threadIdx.x & 127, g = threadIdx.x >> 7;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = g;
-    for (; b + 6 < cs_blocks; b += 8) {
-      a0 += cs_part[(int64_t)b * 128 + r];
-      a1 += cs_part[(int64_t)(b + 2) * 128 + r];
-      a2 += cs_part[(int64_t)(b + 4) * 128 + r];
-      a3 += cs_part[(int64_t)(b + 6) * 128 + r];
+  // ---- column sums: fixed-order two-level tree.  Blocks 0..nsuper-1 each fold a slab of the per-block partials
+  // written by tc_apply_kernel; the last of them to finish (ticket counter) folds the nsuper slab sums and publishes
+  // colsum, the operand exponent, kappa and the ratio-tile exponent.  The result does not depend on which block is last.
+  const int nsuper = min((int)gridDim.x, 32);
+  if ((int)blockIdx.x < nsuper) {
+    __shared__ float partg[256];
+    __shared__ int s_last;
+    const int lanes = R <= 32 ? 32 : (R <= 64 ? 64 : 128);
+    const int groups = 256 / lanes;
+    const int r = threadIdx.x % lanes, g = threadIdx.x / lanes;
+    const int per = (cs_blocks + nsuper - 1) / nsuper;
+    const int b0 = blockIdx.x * per, b1 = min(cs_blocks, b0 + per);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int b = b0 + g;
+    for (; b + 3 * groups < b1; b += 4 * groups) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += cs_part[(int64_t)(b + k * groups) * 128 + r];
     }
-    for (; b < cs_blocks; b += 2) a0 += cs_part[(int64_t)b * 128 + r];
-    part2[g][r] = (a0 + a1) + (a2 + a3);
+    for (; b < b1; b += groups) acc[0] += cs_part[(int64_t)b * 128 + r];
+    partg[threadIdx.x] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     __syncthreads();
-    if (threadIdx.x < 128) {
-      const float mine = part2[0][r] + part2[1][r];
-      if (r < R) colsum[which * R + r] = mine;
-      prod[r] = r < R ? mine * colsum[(1 - which) * R + r] : 0.f;
+    if (threadIdx.x < lanes) {
+      float mine = 0.f;
+      for (int k = 0; k < groups; ++k) mine += partg[k * lanes + threadIdx.x];
+      cs_super[(int64_t)blockIdx.x * 128 + threadIdx.x] = mine;
     }
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      exps[1 + which] = a;
-      *absmax_next = 0u;
-      float dot = 0.f;
-      for (int k = 0; k < 128; ++k) dot += prod[k];
-      const float ptyp = (float)(vconst[0] / (double)dot);
-      int e = 0;
-      const bool ok = ptyp > 0.f && isfinite(ptyp);
-      if (ok) { frexpf(ptyp, &e); e = 1 - e; }     // ptyp * 2^e in [1, 2)
-      exps[3] = e;
-      *kappa = (ok && center) ? ptyp : 0.f;
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)(nsuper - 1)) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __shared__ float prod[128];
+      __threadfence();
+      if (threadIdx.x < 128) {
+        float mine = 0.f;
+        if (threadIdx.x < lanes)
+          for (int k = 0; k < nsuper; ++k) mine += cs_super[(int64_t)k * 128 + threadIdx.x];
+        if (threadIdx.x < R) colsum[which * R + threadIdx.x] = mine;
+        prod[threadIdx.x] = threadIdx.x < R ? mine * colsum[(1 - which) * R + threadIdx.x] : 0.f;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *ticket = 0u;
+        exps[1 + which] = a;
+        *absmax_next = 0u;
+        float dot = 0.f;
+        for (int k = 0; k < 128; ++k) dot += prod[k];
+        const float ptyp = (float)(vconst[0] / (double)dot);
+        int e = 0;
+        const bool ok = ptyp > 0.f && isfinite(ptyp);
+        if (ok) { frexpf(ptyp, &e); e = 1 - e; }     // ptyp * 2^e in [1, 2)
+        exps[3] = e;
+        *kappa = (ok && center) ? ptyp : 0.f;
+      }
     }
   }
 }
@@ -786,7 +835,9 @@ struct TcState {
   float* part = nullptr;
   int64_t part_floats = 0;
   float* colsum = nullptr;          // [2][R]  0 = W, 1 = H
-  float* cs_part = nullptr;         // [<=1024][64]
+  float* cs_part = nullptr;         // [<=1024][128]
+  float* cs_super = nullptr;        // [32][128]
+  unsigned int* ticket = nullptr;
   unsigned int* absmax = nullptr;   // [2 factors][2 parities]
   int* exps = nullptr;              // {v, aW, aH, p}
   double* vpart = nullptr;          // per-block {sum V, sum V log V}
@@ -815,7 +866,7 @@ void tc_destroy(TcState* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part);
-  cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->absmax); cudaFree(s->exps);
+  cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
   cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa); cudaFree(s->trace);
   delete s;
 }
@@ -854,6 +905,9 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->part, (size_t)s->part_floats * 4);
   if (e == cudaSuccess) e = cudaMalloc(&s->colsum, 2 * R * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, 1024 * 128 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->cs_super, 32 * 128 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(s->ticket, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 4 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->vpart, (size_t)s->vblocks * 2 * sizeof(double));
@@ -934,10 +988,10 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   const unsigned grid = (unsigned)ceil_div((s->R & 7) == 0 ? rows * (s->R >> 3) : rows * s->R, 256);
   if (s->split)
     tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
-                                                 s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
+                                                 s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket);
   else
     tc_finish_kernel<false><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
-                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center);
+                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket);
   NMF_LAUNCH_CHECK();
   return 0;
 }
