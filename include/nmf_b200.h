@@ -70,6 +70,9 @@ int nmfb200_nmf_create(nmfb200_ctx** out, int device, int64_t N, int64_t C, int6
 void nmfb200_destroy(nmfb200_ctx* ctx);
 /* which NMFB200_PREC_* the context resolved to */
 int nmfb200_precision(const nmfb200_ctx* ctx);
+/* which NMFB200_PREC_* the contraction kernels use for this beta (the tensor-core path covers beta != 2 for
+ * rank <= 64 and beta == 1 for rank <= 128; everything else runs the fp32 kernels) */
+int nmfb200_precision_for_beta(const nmfb200_ctx* ctx, double beta);
 
 /* Register the target V (device fp32, leading dimension ldv >= C).  Builds the engine-private
  * operand copies and the V-only loss terms.  Replaces nothing in the reference: V is simply the

@@ -154,6 +154,13 @@ void nmfb200_destroy(nmfb200_ctx* ctx) { free_ctx(ctx); }
 
 int nmfb200_precision(const nmfb200_ctx* ctx) { return ctx ? ctx->precision : -100; }
 
+int nmfb200_precision_for_beta(const nmfb200_ctx* ctx, double beta) {
+  if (!ctx) return -100;
+  if (ctx->kind != 0 || !use_tc(ctx, beta)) return NMFB200_PREC_F32;
+  // beta != 1 kernels read only the hi halves of the operand copies
+  return beta == 1.0 ? ctx->precision : NMFB200_PREC_F16;
+}
+
 int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* stream) {
   CTX_GUARD(ctx, 0);
   if (!V || ldv < ctx->C) return fail(NMFB200_ERR_INVALID, "bad target pointer / leading dimension");

@@ -51,9 +51,12 @@ struct TcKernelParams {
   int Mr, Nc;                 // valid rows of F / rows of G (= columns of Vm)
   int row_blocks, tiles, nchunks, tiles_per_chunk;
   float* part;                // [nchunks][Mr][ldp] fp32 numerators
+  float* part2;               // [nchunks][Mr][ldp] fp32 denominators (beta != 1 kernels)
+  float bm1, bm2;             // beta - 1, beta - 2 (generic-beta kernel)
   int64_t chunk_stride;
   int ldp;
-  const int* exps;            // device: {v, aW, aH, p}: power-of-two exponents of V16, W16, H16 and of the ratio tile P
+  const int* exps;            // device: {v, aW, aH, p, pn, pd}: power-of-two exponents of V16, W16, H16, of the KL ratio
+                              // tile P, and of the two beta != 1 tiles Pn, Pp
   int ef, eg;                 // which of exps[] belong to F and G
   double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
   const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
@@ -82,15 +85,26 @@ struct SmemLayout {
   static constexpr int kTotal = kLossSlots + 16 * 8;
 };
 
-template <class C, bool LOSS>
+// BM selects the phi stage (nmf.py:61-74): 0 = beta 1 (one centred ratio tile, one accumulator); otherwise two tiles
+// Pn = V x^(beta-2), Pp = x^(beta-1) and two accumulators (numerator, denominator): 1 = beta 0, 2 = beta 0.5,
+// 3 = beta 1.5, 4 = any other beta (lg2/ex2).
+enum : int { kBmKL = 0, kBmIS = 1, kBm05 = 2, kBm15 = 3, kBmGen = 4 };
+
+template <class C, int BM, bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
   constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS, AHEAD = C::AHEAD;
   constexpr bool SPLIT = C::SPLIT;
-  constexpr uint32_t kColO = NS * TN;
+  constexpr bool TWO = BM != kBmKL;
+  // TMEM columns.  one-output: S/P stages [0, NS TN) | O [NS TN, NS TN + KW).
+  //               two-output: S/Pn stages [0, 256) | Pp stages [256, 384) | O_num [384, 448) | O_den [448, 512)
+  constexpr uint32_t kColPp = NS * TN;
+  constexpr uint32_t kColO = TWO ? 384 : NS * TN;
+  constexpr uint32_t kColO2 = 448;
   using L = SmemLayout<KW, TN, NF, NG, NV, NS>;
-  static_assert(NS * TN + KW <= (int)kTmemCols, "TMEM budget");
+  static_assert(TWO || NS * TN + KW <= (int)kTmemCols, "TMEM budget");
+  static_assert(!TWO || (!SPLIT && RP == 64 && TN == 128 && NS == 2 && !LOSS), "two-output kernels: fast mode, R <= 64");
   static_assert(TN == 64 || TN == 128, "tile width");
   static_assert(RP == 64 || RP == 128, "padded rank");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -273,9 +287,13 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             const uint32_t aP = tmem + kColS + os * TN;
             if (ptx::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < TN / 16; ++ks)
+              for (int ks = 0; ks < TN / 16; ++ks) {
                 ptx::mma_ts(tmem + kColO, aP + ks * 8, ptx::make_desc(blo + ks * 128, descHi), idescO,
                             (first && ks == 0) ? 0u : 1u);
+                if (TWO)
+                  ptx::mma_ts(tmem + kColO2, tmem + kColPp + os * 64 + ks * 8, ptx::make_desc(blo + ks * 128, descHi),
+                              idescO, (first && ks == 0) ? 0u : 1u);
+              }
               ptx::mma_commit(BAR(B_GEMPTY + og));
               if (last) ptx::mma_commit(BAR(B_OFULL));
             }
@@ -310,14 +328,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     const int ev = p.exps[0], ea = p.exps[p.ef], eb = p.exps[p.eg], ep = p.exps[3];
     // update: x' = (S + eps) * 2^(v-p), so P~ = V~ / x' = P * 2^p (P ~ 1 maps to ~1: fp16-safe for any input scale)
     // loss  : x  = S + eps in true scale
-    const float c1 = LOSS ? exp2f((float)(-ea - eb)) : exp2f((float)(ev - ea - eb - ep));
-    const float c2 = LOSS ? kEps : kEps * exp2f((float)(ev - ep));
+    const float c1 = (LOSS || TWO) ? exp2f((float)(-ea - eb)) : exp2f((float)(ev - ea - eb - ep));
+    const float c2 = (LOSS || TWO) ? kEps : kEps * exp2f((float)(ev - ep));
+    // two-output kernels: Pn~ = V~ x^(beta-2) kn, Pp~ = x^(beta-1) kd with x = S + eps in true scale
+    const float kn = TWO ? exp2f((float)(p.exps[4] - ev)) : 0.f;
+    const float kd = TWO ? exp2f((float)p.exps[5]) : 0.f;
     // The tile fed to MMA-2 is the CENTRED ratio (P - kappa) 2^p with kappa = sum(V) / sum(W H^T) (-> 1 as the fit
     // converges); kappa * colsum(G) is added back in fp32 by the ratio stage.  Tensor-core accumulation truncates
     // (measured: -4.7e-5 relative on this all-positive sum, profiles/README.md), a one-signed bias that the
     // scale-free direction (W a, H / a) of KL-NMF integrates over iterations; the centred sum is signed and
     // small, and its fp16 rounding error is relative to |P - kappa| instead of |P|.
-    const float negpc = LOSS ? 0.f : -(*p.kappa) * exp2f((float)ep);
+    const float negpc = (LOSS || TWO) ? 0.f : -(*p.kappa) * exp2f((float)ep);
     double accA = 0.0, accB = 0.0;
     uint32_t t = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -363,6 +384,34 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             }
             accA += (double)la;
             accB += (double)lb;
+          } else if (TWO) {
+            uint32_t pn[16], pp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+              float fn[2], fp[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float x = fmaf(__uint_as_float(sreg[2 * i + e]), c1, c2);        // WH + eps, nmf.py:68,72
+                if (BM == kBmIS) {                 // nmf.py:68-70
+                  const float r = ptx::rcp_approx(x);
+                  fp[e] = r; fn[e] = r * r;
+                } else if (BM == kBm05) {          // x^-0.5, x^-1.5
+                  const float rs = rsqrtf(x);
+                  fp[e] = rs; fn[e] = rs * rs * rs;
+                } else if (BM == kBm15) {          // x^0.5, x^-0.5
+                  const float rs = rsqrtf(x);
+                  fp[e] = x * rs; fn[e] = rs;
+                } else {                           // nmf.py:72-74
+                  const float l = __log2f(x);
+                  fp[e] = exp2f(p.bm1 * l); fn[e] = exp2f(p.bm2 * l);
+                }
+              }
+              pn[i] = ptx::pack_f16x2_sat(vf.x * fn[0] * kn, vf.y * fn[1] * kn);
+              pp[i] = ptx::pack_f16x2_sat(fp[0] * kd, fp[1] * kd);
+            }
+            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, pn);
+            ptx::tmem_st16(tmem + lane_addr + kColPp + st * 64 + c4 * 16, pp);
           } else {
             uint32_t preg[16];
 #pragma unroll
@@ -397,7 +446,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float oscale = exp2f(-(float)(p.exps[p.eg] + p.exps[3]));      // O = sum (P 2^p) (G 2^eg)
+    const float oscale = exp2f(-(float)(p.exps[p.eg] + p.exps[TWO ? 4 : 3]));      // O = sum (P 2^p) (G 2^eg)
+    const float oscale2 = TWO ? exp2f(-(float)(p.exps[p.eg] + p.exps[5])) : 0.f;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int rb = item % p.row_blocks, chunk = item / p.row_blocks;
@@ -405,6 +455,29 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       ptx::tc_fence_after();
       const int64_t grow = (int64_t)rb * kTileM + row;
       float* dst = p.part + (int64_t)chunk * p.chunk_stride + grow * p.ldp;
+      if (TWO) {
+        // numerator then denominator accumulator (64 columns each); O is handed back after the last TMEM load
+        float* dst2 = p.part2 + (int64_t)chunk * p.chunk_stride + grow * p.ldp;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float o[64];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            ptx::tmem_ld32(tmem + lane_addr + (half ? kColO2 : kColO) + c * 32, raw);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]) * (half ? oscale2 : oscale);
+          }
+          if (half == 1) { ptx::tc_fence_before(); ptx::mbar_arrive(BAR(B_OEMPTY)); }
+          if (grow < p.Mr) {
+            float* d = half ? dst2 : dst;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          }
+        }
+        continue;
+      }
       if (RP == 64) {
         // whole O row (64 values) into registers, hand the accumulator back to the MMA warp, then store
         float o[64];
@@ -549,6 +622,7 @@ reduce_vconst_kernel(const double* __restrict__ vpart, int64_t nblk, double* __r
 struct TcApplyArgs {
   float* param; int64_t rows; int R; int rpb;
   const float* num; int nchunks; int64_t chunk_stride; int Rp;     // partial row pitch = padded rank
+  const float* den;          // beta != 1: partial denominators (same layout); nullptr for beta == 1
   const float* kl_den; float gamma, l1, l2;
   float* cs_part;            // [gridDim.x][128]
   const float* kappa;        // the kernel accumulated sum (P - kappa) G: add kappa * colsum(G) back
@@ -564,17 +638,24 @@ tc_apply_kernel(TcApplyArgs a) {
   const int64_t row1 = min(a.rows, row0 + a.rpb);
   float cs = 0.f, mx = 0.f;
   if (r < a.R) {
-    const float klden = a.apply ? a.kl_den[r] : 1.f;
-    const float kap = a.apply ? *a.kappa : 0.f;
+    const float klden = (a.apply && !a.den) ? a.kl_den[r] : 1.f;
+    const float kap = (a.apply && !a.den) ? *a.kappa : 0.f;
     for (int64_t row = row0 + rg; row < row1; row += 2) {
       const int64_t idx = row * a.R + r;
       float v = a.param[idx];
       if (a.apply) {
         float num = 0.f;
         for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * a.Rp + r];
-        num = fmaf(kap, klden, num);                            // the kernel accumulated sum (P - kappa) G
+        float pos;
+        if (a.den) {
+          float den = 0.f;
+          for (int ch = 0; ch < a.nchunks; ++ch) den += a.den[ch * a.chunk_stride + row * a.Rp + r];
+          pos = fmaxf(den, 0.f) + kEps;                         // nmf.py:83
+        } else {
+          num = fmaf(kap, klden, num);                          // the kernel accumulated sum (P - kappa) G
+          pos = klden;                                          // nmf.py:368-369 / :381-382
+        }
         const float neg = fmaxf(num, 0.f) + kEps;              // nmf.py:78
-        float pos = klden;                                      // nmf.py:368-369 / :381-382
         if (a.l1 > 0.f) pos += a.l1;                            // nmf.py:85-86
         if (a.l2 > 0.f) pos = fmaf(a.l2, v, pos);               // nmf.py:87-88
         float mult = neg / pos;                                 // nmf.py:89
@@ -608,7 +689,7 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
   if (rl < rows_per_pass) {
     float4 kd = make_float4(1.f, 1.f, 1.f, 1.f);
     float kap = 0.f;
-    if (a.apply) { kd = *reinterpret_cast<const float4*>(a.kl_den + 4 * q); kap = *a.kappa; }
+    if (a.apply && !a.den) { kd = *reinterpret_cast<const float4*>(a.kl_den + 4 * q); kap = *a.kappa; }
     for (int64_t row = row0 + rl; row < row1; row += rows_per_pass) {
       float4* pp = reinterpret_cast<float4*>(a.param + row * a.R) + q;
       float4 v = *pp;
@@ -618,12 +699,20 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
           const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * a.Rp) + q);
           num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
         }
+        float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.den) {
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            const float4 t = *(reinterpret_cast<const float4*>(a.den + ch * a.chunk_stride + row * a.Rp) + q);
+            dsum.x += t.x; dsum.y += t.y; dsum.z += t.z; dsum.w += t.w;
+          }
+        }
         float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
+        const float ds[4] = {dsum.x, dsum.y, dsum.z, dsum.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float n = fmaf(kap, dd[i], nn[i]);                  // the kernel accumulated sum (P - kappa) G
+          const float n = a.den ? nn[i] : fmaf(kap, dd[i], nn[i]);  // beta == 1: the kernel accumulated sum (P - kappa) G
           const float neg = fmaxf(n, 0.f) + kEps;                   // nmf.py:78
-          float pos = dd[i];                                        // nmf.py:368-369 / :381-382
+          float pos = a.den ? fmaxf(ds[i], 0.f) + kEps : dd[i];     // nmf.py:83 | nmf.py:368-369 / :381-382
           if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
           if (a.l2 > 0.f) pos = fmaf(a.l2, vv[i], pos);             // nmf.py:87-88
           float mult = neg / pos;                                   // nmf.py:89
@@ -661,7 +750,8 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
                  const unsigned int* __restrict__ absmax, unsigned int* __restrict__ absmax_next,
                  int* __restrict__ exps, int which, const float* __restrict__ cs_part, int cs_blocks,
                  float* __restrict__ colsum /* [2][R] */, const double* __restrict__ vconst,
-                 float* __restrict__ kappa, int center, float* __restrict__ cs_super, unsigned int* __restrict__ ticket) {
+                 float* __restrict__ kappa, int center, float* __restrict__ cs_super, unsigned int* __restrict__ ticket,
+                 float bm1, float bm2, double cells) {
   const int a = pow2_exp_for(__uint_as_float(*absmax));
   const float sc = exp2f((float)a);
   if ((R & 7) == 0) {
@@ -747,6 +837,17 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
         if (ok) { frexpf(ptyp, &e); e = 1 - e; }     // ptyp * 2^e in [1, 2)
         exps[3] = e;
         *kappa = (ok && center) ? ptyp : 0.f;
+        // beta != 1: typical x = mean(WH), typical Pn = mean(V) x^(beta-2), Pp = x^(beta-1) -> both tiles near 2^0
+        const float xbar = (float)((double)dot / cells), vbar = (float)(vconst[0] / cells);
+        int en = 0, ed = 0;
+        if (xbar > 0.f && isfinite(xbar)) {
+          const float lx = log2f(xbar);
+          const float ln = (vbar > 0.f ? log2f(vbar) : 0.f) + bm2 * lx, ld = bm1 * lx;
+          if (isfinite(ln)) en = -(int)rintf(ln);
+          if (isfinite(ld)) ed = -(int)rintf(ld);
+        }
+        exps[4] = en;
+        exps[5] = ed;
       }
     }
   }
@@ -833,6 +934,7 @@ struct TcState {
   int64_t ldc = 0, ldn = 0;
   __half *V16 = nullptr, *Vt16 = nullptr, *W16 = nullptr, *H16 = nullptr;
   float* part = nullptr;
+  float* part2 = nullptr;           // denominators of the beta != 1 kernels (allocated on first use)
   int64_t part_floats = 0;
   float* colsum = nullptr;          // [2][R]  0 = W, 1 = H
   float* cs_part = nullptr;         // [<=1024][128]
@@ -865,7 +967,7 @@ bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
 void tc_destroy(TcState* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part);
+  cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
   cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa); cudaFree(s->trace);
   delete s;
@@ -909,7 +1011,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(s->ticket, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 4 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&s->exps, 8 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->vpart, (size_t)s->vblocks * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->vconst, 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->num_sms * 2 * sizeof(double));
@@ -917,7 +1019,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMemset(s->kappa, 0, sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(s->W16, 0, (size_t)C * s->KW * 2);
   if (e == cudaSuccess) e = cudaMemset(s->H16, 0, (size_t)N * s->KW * 2);
-  if (e == cudaSuccess) e = cudaMemset(s->exps, 0, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(s->exps, 0, 8 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(s->absmax, 0, 4 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(s->colsum, 0, 2 * R * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(s->vconst, 0, 2 * sizeof(double));
@@ -938,7 +1040,11 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   return 0;
 }
 
-bool tc_supports_beta(const TcState*, double beta) { return beta == 1.0; }
+bool tc_supports_beta(const TcState* s, double beta) {
+  if (beta == 1.0) return true;
+  // beta != 1: two-output kernel (rank <= 64); beta == 2 stays on the fp32 path (its ratio tiles are V and WH themselves)
+  return beta != 2.0 && s->Rp == 64 && s->TN == 128;
+}
 bool tc_supports_loss(const TcState*, double beta) { return beta == 1.0; }
 
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st) {
@@ -964,8 +1070,8 @@ namespace {
 
 // ratio stage (apply != 0) or plain re-scan (apply == 0) of one factor, then rebuild its fp16 operand copy,
 // column sums and the exponents that depend on it: two launches.
-int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double gamma, double l1,
-                     double l2, cudaStream_t st) {
+int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double beta, double gamma,
+                     double l1, double l2, cudaStream_t st) {
   const int64_t rows = which == 0 ? s->C : s->N;
   int rpb = (int)round_up(ceil_div(rows, 1024), 4);
   if (rpb < 64) rpb = 64;
@@ -977,6 +1083,7 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   a.param = param; a.rows = rows; a.R = (int)s->R; a.rpb = rpb;
   a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * s->Rp; a.Rp = s->Rp;
   a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
+  a.den = (apply && beta != 1.0) ? s->part2 : nullptr;
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = s->kappa;
   if ((s->R & 3) == 0)
@@ -988,24 +1095,26 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   const unsigned grid = (unsigned)ceil_div((s->R & 7) == 0 ? rows * (s->R >> 3) : rows * s->R, 256);
   if (s->split)
     tc_finish_kernel<true><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
-                                                 s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket);
+                                                 s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket,
+                                                 (float)(beta - 1.0), (float)(beta - 2.0), (double)s->N * (double)s->C);
   else
     tc_finish_kernel<false><<<grid, 256, 0, st>>>(param, rows, (int)s->R, out, s->KW, s->Rp, slot, next, s->exps, which,
-                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket);
+                                                  s->cs_part, blocks, s->colsum, s->vconst, s->kappa, s->center, s->cs_super, s->ticket,
+                                                 (float)(beta - 1.0), (float)(beta - 2.0), (double)s->N * (double)s->C);
   NMF_LAUNCH_CHECK();
   return 0;
 }
 
-int ensure_synced(TcState* s, const float* W, const float* H, cudaStream_t st) {
+int ensure_synced(TcState* s, const float* W, const float* H, double beta, cudaStream_t st) {
   if (!s->has_target) { set_error("tensor-core path: set_target has not been called"); return 3; }
   const bool both = s->dirty_w && s->dirty_h;
   if (s->dirty_w) {
-    int rc = apply_and_finish(s, 0, const_cast<float*>(W), false, nullptr, 1, 0, 0, st);
+    int rc = apply_and_finish(s, 0, const_cast<float*>(W), false, nullptr, beta, 1, 0, 0, st);
     if (rc) return rc;
     s->dirty_w = false;
   }
   if (s->dirty_h) {
-    int rc = apply_and_finish(s, 1, const_cast<float*>(H), false, nullptr, 1, 0, 0, st);
+    int rc = apply_and_finish(s, 1, const_cast<float*>(H), false, nullptr, beta, 1, 0, 0, st);
     if (rc) return rc;
     s->dirty_h = false;
   }
@@ -1013,11 +1122,11 @@ int ensure_synced(TcState* s, const float* W, const float* H, cudaStream_t st) {
   return 0;
 }
 
-template <class C, bool LOSS>
-int launch_contract_t(TcState* s, int which, cudaStream_t st) {
+template <class C, int BM, bool LOSS>
+int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   using L = SmemLayout<C::KW, C::TN, C::NF, C::NG, C::NV, C::NS>;
   static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
-  auto kern = tc_contract_kernel<C, LOSS>;
+  auto kern = tc_contract_kernel<C, BM, LOSS>;
   static bool attr_set = false;
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
   if (!attr_set) {
@@ -1031,6 +1140,7 @@ int launch_contract_t(TcState* s, int which, cudaStream_t st) {
   p.Nc = (int)(which == 0 ? s->N : s->C);
   p.row_blocks = pl.row_blocks; p.tiles = pl.tiles; p.nchunks = pl.nchunks; p.tiles_per_chunk = pl.tpc;
   p.part = s->part; p.chunk_stride = (int64_t)p.Mr * s->Rp; p.ldp = s->Rp;
+  p.part2 = s->part2; p.bm1 = (float)(beta - 1.0); p.bm2 = (float)(beta - 2.0);
   p.exps = s->exps;
   p.ef = which == 0 ? 1 : 2;
   p.eg = which == 0 ? 2 : 1;
@@ -1058,18 +1168,32 @@ using CfgSplit64N = Cfg<64, true, 64, 1, 6, 6, 4, 2>;       // (variant 1) 64-co
 using CfgFast128 = Cfg<128, false, 128, 1, 3, 3, 3, 1>;     // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
 using CfgSplit128 = Cfg<128, true, 64, 1, 3, 4, 4, 1>;      // F 64 | G 3x32 | V 4x16 KB     ; TMEM 4x64 + 256
 
+using CfgTwo64 = Cfg<64, false, 128, 2, 3, 4, 2, 1>;        // beta != 1: F 2x16 | G 3x16 | V 4x32 KB ; TMEM 2x128 + 128 + 2x64
+
 template <bool LOSS>
 int launch_contract_any(TcState* s, int which, cudaStream_t st) {
   if (s->Rp == 64) {
-    if (!s->split) return launch_contract_t<CfgFast64, LOSS>(s, which, st);
-    if (s->TN == 64) return launch_contract_t<CfgSplit64N, LOSS>(s, which, st);
-    return launch_contract_t<CfgSplit64, LOSS>(s, which, st);
+    if (!s->split) return launch_contract_t<CfgFast64, kBmKL, LOSS>(s, which, 1.0, st);
+    if (s->TN == 64) return launch_contract_t<CfgSplit64N, kBmKL, LOSS>(s, which, 1.0, st);
+    return launch_contract_t<CfgSplit64, kBmKL, LOSS>(s, which, 1.0, st);
   }
-  if (!s->split) return launch_contract_t<CfgFast128, LOSS>(s, which, st);
-  return launch_contract_t<CfgSplit128, LOSS>(s, which, st);
+  if (!s->split) return launch_contract_t<CfgFast128, kBmKL, LOSS>(s, which, 1.0, st);
+  return launch_contract_t<CfgSplit128, kBmKL, LOSS>(s, which, 1.0, st);
 }
 
-int launch_contract(TcState* s, int which, cudaStream_t st) {
+// beta != 1 (and != 2): two-output kernel on the hi halves of the operand copies
+int launch_contract_two(TcState* s, int which, double beta, cudaStream_t st) {
+  if (!s->part2) NMF_CUDA_CHECK(cudaMalloc(&s->part2, (size_t)s->part_floats * 4));
+  int g;
+  if (beta == 0.0) g = launch_contract_t<CfgTwo64, kBmIS, false>(s, which, beta, st);
+  else if (beta == 0.5) g = launch_contract_t<CfgTwo64, kBm05, false>(s, which, beta, st);
+  else if (beta == 1.5) g = launch_contract_t<CfgTwo64, kBm15, false>(s, which, beta, st);
+  else g = launch_contract_t<CfgTwo64, kBmGen, false>(s, which, beta, st);
+  return g > 0 ? 0 : 2;
+}
+
+int launch_contract(TcState* s, int which, double beta, cudaStream_t st) {
+  if (beta != 1.0) return launch_contract_two(s, which, beta, st);
   return launch_contract_any<false>(s, which, st) > 0 ? 0 : 2;
 }
 
@@ -1077,33 +1201,32 @@ int launch_contract(TcState* s, int which, cudaStream_t st) {
 
 int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,
                 cudaStream_t st) {
-  (void)beta;
-  int rc = ensure_synced(s, W, H, st);
+  int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, 0, st);
+  rc = launch_contract(s, 0, beta, st);
   if (rc) return rc;
-  return apply_and_finish(s, 0, W, true, &s->plan_w, gamma, l1, l2, st);
+  return apply_and_finish(s, 0, W, true, &s->plan_w, beta, gamma, l1, l2, st);
 }
 
 int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
                 cudaStream_t st) {
-  (void)beta;
-  int rc = ensure_synced(s, W, H, st);
+  int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, 1, st);
+  rc = launch_contract(s, 1, beta, st);
   if (rc) return rc;
-  return apply_and_finish(s, 1, H, true, &s->plan_h, gamma, l1, l2, st);
+  return apply_and_finish(s, 1, H, true, &s->plan_h, beta, gamma, l1, l2, st);
 }
 
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st) {
-  (void)beta;
-  int rc = ensure_synced(s, W, H, st);
+  int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, 0, st);
+  rc = launch_contract(s, 0, beta, st);
   if (rc) return rc;
   const int64_t CR = s->C * s->R;
   rc = reduce_chunks(s->part, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp, partial, st);
   if (rc) return rc;
+  if (beta != 1.0)      // raw denominator partial follows the numerator (include/nmf_b200.h)
+    return reduce_chunks(s->part2, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp, partial + CR, st);
   NMF_CUDA_CHECK(cudaMemcpyAsync(partial + CR, s->colsum + s->R, s->R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // the kernel accumulated sum_n (P - kappa) H: add kappa * colsum(H_local) back
   add_rowvec_kernel<<<(unsigned)ceil_div(CR, 256), 256, 0, st>>>(partial, CR, (int)s->R, s->colsum + s->R, s->kappa);
@@ -1127,10 +1250,9 @@ int tc_check_wait_abort(cudaStream_t st) {
 }
 
 int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st) {
-  (void)beta;
-  int rc = ensure_synced(s, W, H, st);
+  int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, which, st);
+  rc = launch_contract(s, which, beta, st);
   if (rc == 0 && getenv("NMFB200_TC_CHECK")) {
     if (tc_check_wait_abort(st) > 0) { set_error("mbarrier wait aborted (protocol bug)"); return 2; }
   }
@@ -1150,8 +1272,7 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
 }
 
 int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {
-  (void)beta;
-  int rc = ensure_synced(s, W, H, st);
+  int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
   // S = H W^T over the H-update decomposition (row blocks of H, tiles of W), no second GEMM
   int grid = launch_contract_any<true>(s, 1, st);

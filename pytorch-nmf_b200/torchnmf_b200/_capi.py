@@ -26,6 +26,7 @@ SIGNATURES = {
     "nmfb200_nmf_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _int]),
     "nmfb200_destroy": (None, [_vp]),
     "nmfb200_precision": (_int, [_vp]),
+    "nmfb200_precision_for_beta": (_int, [_vp, _dbl]),
     "nmfb200_nmf_set_target": (_int, [_vp, _vp, _i64, _vp]),
     "nmfb200_target_minmax": (_int, [_vp, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _vp]),
     "nmfb200_nmf_sync_factors": (_int, [_vp, _vp, _vp, _vp]),

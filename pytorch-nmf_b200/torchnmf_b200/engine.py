@@ -87,6 +87,10 @@ class _CudaEngine:
     def precision(self):
         return _capi.PRECISION_NAMES[self._lib.nmfb200_precision(self._ctx)]
 
+    def precision_for(self, beta):
+        """Arithmetic the contraction kernels use for this beta ("f32" when the tensor-core path does not cover it)."""
+        return _capi.PRECISION_NAMES[self._lib.nmfb200_precision_for_beta(self._ctx, float(beta))]
+
     def minmax(self):
         vmin, vmax = ctypes.c_float(), ctypes.c_float()
         _capi.check(self._lib.nmfb200_target_minmax(self._ctx, ctypes.byref(vmin), ctypes.byref(vmax),
@@ -215,6 +219,9 @@ class ShardedEngine:
     @property
     def precision(self):
         return self.local.precision
+
+    def precision_for(self, beta):
+        return self.local.precision_for(beta) if hasattr(self.local, "precision_for") else self.local.precision
 
     def close(self):
         self.local.close()

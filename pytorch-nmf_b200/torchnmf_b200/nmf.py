@@ -199,7 +199,7 @@ class BaseComponent(torch.nn.Module):
             if staged:
                 W.data.copy_(Wd)
                 H.data.copy_(Hd)
-            self.last_fit_precision = eng.precision
+            self.last_fit_precision = eng.precision_for(beta) if hasattr(eng, "precision_for") else eng.precision
         finally:
             eng.close()
         return n_iter + 1                                                                  # nmf.py:409

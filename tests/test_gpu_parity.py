@@ -266,3 +266,35 @@ def test_tc_loss_matches_oracle(precision):
     got = eng.loss(1)
     eng.close()
     assert math.isclose(got, want, rel_tol=5e-5), (got, want)
+
+
+# ---- beta != 1 on tensor cores (two-output kernels: numerator and denominator accumulators) -------------------
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1.5, 3])
+@pytest.mark.parametrize("shape", [(384, 256, 64), (1000, 700, 20), (130, 2049, 33)])
+def test_tc_two_output_updates_match_oracle(beta, shape):
+    N, C, R = shape
+    torch.manual_seed(N + C + R)
+    V = torch.rand(N, C) + 0.01
+    W0 = torch.rand(C, R) + 0.05
+    H0 = torch.rand(N, R) * 3 + 0.01
+    from torchnmf_b200.engine import CudaNmfEngine
+    Wd, Hd = W0.cuda(), H0.cuda()
+    eng = CudaNmfEngine(V.cuda(), Wd, Hd, "f16_split")
+    g = orc.gamma_of(beta)
+    eng.update_w(beta, g, 0.0, 0.0)
+    Wn = orc.nmf_update_w(V, W0, H0, beta)
+    eng.update_h(beta, g, 0.01, 0.02)
+    Hn = orc.nmf_update_h(V, Wn, H0, beta, g, 0.01, 0.02)
+    eng.close()
+    assert _close(Wd.cpu(), Wn, 1e-3, 1e-5)[0], _close(Wd.cpu(), Wn, 1e-3, 1e-5)[1]
+    assert _close(Hd.cpu(), Hn, 1e-3, 1e-5)[0], _close(Hd.cpu(), Hn, 1e-3, 1e-5)[1]
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("nmf_b") and "_b1_" not in n and "_b2_" not in n])
+def test_tc_two_output_fit_matches_reference_golden(name):
+    c = CASES[name]
+    m, n_iter = _run_case(c, "f16")
+    assert n_iter == c["n_iter"]
+    for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
+        ok, err = _close(got, want, 2e-3, 1e-5)           # 20 iterations, fp16 ratio tiles, single-rounded factors
+        assert ok, f"{name} {nm}: scaled err {err:.3e}"
