@@ -96,7 +96,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
   constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS, AHEAD = C::AHEAD;
   constexpr bool SPLIT = C::SPLIT;
-  constexpr bool TWO = BM != kBmKL;
+  constexpr bool TWO = BM != kBmKL && !LOSS;     // LOSS kernels only need S, whatever the beta
   // TMEM columns.  one-output: S/P stages [0, NS TN) | O [NS TN, NS TN + KW).
   //               two-output: S/Pn stages [0, 256) | Pp stages [256, 384) | O_num [384, 448) | O_den [448, 512)
   constexpr uint32_t kColPp = NS * TN;
@@ -104,7 +104,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   constexpr uint32_t kColO2 = 448;
   using L = SmemLayout<KW, TN, NF, NG, NV, NS>;
   static_assert(TWO || NS * TN + KW <= (int)kTmemCols, "TMEM budget");
-  static_assert(!TWO || (!SPLIT && RP == 64 && TN == 128 && NS == 2 && !LOSS), "two-output kernels: fast mode, R <= 64");
+  static_assert(!TWO || (!SPLIT && RP == 64 && TN == 128 && NS == 2), "two-output kernels: fast mode, R <= 64");
   static_assert(TN == 64 || TN == 128, "tile width");
   static_assert(RP == 64 || RP == 128, "padded rank");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -341,11 +341,13 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     const float negpc = (LOSS || TWO) ? 0.f : -(*p.kappa) * exp2f((float)ep);
     double accA = 0.0, accB = 0.0;
     uint32_t t = 0;
+    const float vinv = exp2f(-(float)ev);
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int chunk = item / p.row_blocks;
       const int tb = chunk * p.tiles_per_chunk;
       const int te = min(p.tiles, tb + p.tiles_per_chunk);
       const int n = te - tb;
+      const bool row_ok = (item % p.row_blocks) * kTileM + row < p.Mr;
       for (int j = 0; j < n; ++j) {
         const uint32_t tt = t + j;
         if ((int)(tt & 1) != g) continue;
@@ -372,7 +374,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           }
           ptx::tc_wait_ld();
           const uint32_t* vw = reinterpret_cast<const uint32_t*>(vv);
-          if (LOSS) {
+          if (LOSS && BM == kBmKL) {
             float la = 0.f, lb = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -381,6 +383,35 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
               la = fmaf(vf.x, __log2f(fmaf(s0, c1, c2)), la);
               la = fmaf(vf.y, __log2f(fmaf(s1, c1, c2)), la);
               lb += s0 + s1;
+            }
+            accA += (double)la;
+            accB += (double)lb;
+          } else if (LOSS) {
+            // metrics.py:56-57 (beta 0) and :84-96 (generic): A = sum t x^(beta-1), B = sum x^beta (beta 0: sum ln x / ln 2).
+            // Out-of-range rows / columns are zero-filled operands (x = eps there) and must be masked out.
+            float la = 0.f, lb = 0.f;
+            const int col0 = (tb + j) * TN + c4 * 32;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const bool ok = row_ok && col0 + 2 * i + e < p.Nc;
+                const float x = fmaf(__uint_as_float(sreg[2 * i + e]), c1, c2);
+                const float v = (e ? vf.y : vf.x) * vinv;
+                const float lx = __log2f(x);
+                float ta, tb2;
+                if (BM == kBmIS) {
+                  ta = (v + kEps) * ptx::rcp_approx(x);
+                  tb2 = lx;
+                } else {
+                  const float tv = p.bm1 < -1.f ? v + kEps : v;          // beta < 0: target + eps (metrics.py:87-88)
+                  ta = tv * exp2f(p.bm1 * lx);
+                  tb2 = exp2f((p.bm1 + 1.f) * lx);
+                }
+                la += ok ? ta : 0.f;
+                lb += ok ? tb2 : 0.f;
+              }
             }
             accA += (double)la;
             accB += (double)lb;
@@ -869,6 +900,41 @@ __global__ void tc_loss_final_kernel(const double* __restrict__ part, int nblk, 
   *out = vconst[1] - vconst[0] - ln2 * exp2((double)-exps[0]) * a + exp2((double)-(exps[1] + exps[2])) * b;
 }
 
+// beta != 1 (metrics.py:56-57, :84-96): vb = the V-only term for this beta (sum ln(V+eps) or sum t^beta)
+__global__ void tc_loss_final_beta_kernel(const double* __restrict__ part, int nblk, const double* __restrict__ vb,
+                                          double beta, double cells, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblk; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+  const double ln2 = 0.693147180559945309417;
+  if (beta == 0.0) *out = a - *vb + ln2 * b - cells;
+  else *out = (*vb + (beta - 1.0) * b - beta * a) / (beta * (beta - 1.0));
+}
+
+// V-only loss term: beta == 0: sum ln(V + eps); else sum t^beta with t = V (+ eps if beta < 0).  Two-level, fixed order.
+__global__ void __launch_bounds__(256)
+v_beta_term_kernel(const float* __restrict__ V, int64_t rows, int64_t cols, int64_t ld, float beta,
+                   double* __restrict__ blockpart) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float v = V[r * ld + c];
+    acc += (double)(beta == 0.f ? logf(v + kEps) : powf(beta < 0.f ? v + kEps : v, beta));
+  }
+  const double t = block_sum256(acc, red);
+  if (threadIdx.x == 0) blockpart[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(256)
+sum_blocks_kernel(const double* __restrict__ blockpart, int n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += blockpart[i];
+  const double t = block_sum256(acc, red);
+  if (threadIdx.x == 0) *out = t;
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -946,6 +1012,11 @@ struct TcState {
   int64_t vblocks = 0;
   double* vconst = nullptr;         // {sum V, sum V log(V+eps)}
   double* loss_part = nullptr;      // [num_sms][2]
+  const float* Vsrc = nullptr;      // the registered fp32 target (borrowed) for the V-only loss terms
+  int64_t ldv = 0;
+  double* vbeta = nullptr;          // device: V-only loss term of beta `vbeta_for`
+  double* vbeta_part = nullptr;     // [1024]
+  double vbeta_for = 1.0;           // 1.0 = none cached
   CUtensorMap tmV, tmVt;            // V16 / Vt16, box 64 x 128
   CUtensorMap tmWf, tmHf;           // factors as the row factor F: box 64 x 128
   CUtensorMap tmWg, tmHg;           // factors as the column factor G: box 64 x TN
@@ -969,7 +1040,7 @@ void tc_destroy(TcState* s) {
   cudaSetDevice(s->device);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
-  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->kappa); cudaFree(s->trace);
+  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->trace);
   delete s;
 }
 
@@ -1016,6 +1087,8 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->vconst, 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->num_sms * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->vbeta, sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->vbeta_part, 1024 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(s->kappa, 0, sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(s->W16, 0, (size_t)C * s->KW * 2);
   if (e == cudaSuccess) e = cudaMemset(s->H16, 0, (size_t)N * s->KW * 2);
@@ -1045,7 +1118,7 @@ bool tc_supports_beta(const TcState* s, double beta) {
   // beta != 1: two-output kernel (rank <= 64); beta == 2 stays on the fp32 path (its ratio tiles are V and WH themselves)
   return beta != 2.0 && s->Rp == 64 && s->TN == 128;
 }
-bool tc_supports_loss(const TcState*, double beta) { return beta == 1.0; }
+bool tc_supports_loss(const TcState* s, double beta) { return tc_supports_beta(s, beta); }
 
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st) {
   set_vexp_kernel<<<1, 32, 0, st>>>(minmax_dev, s->exps);
@@ -1057,6 +1130,7 @@ int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_d
   reduce_vconst_kernel<<<1, 256, 0, st>>>(s->vpart, s->vblocks, s->vconst);
   NMF_LAUNCH_CHECK();
   s->has_target = true;
+  s->Vsrc = V; s->ldv = ldv; s->vbeta_for = 1.0;
   s->dirty_w = s->dirty_h = true;      // exps[3] depends on sum(V)
   return 0;
 }
@@ -1181,6 +1255,17 @@ int launch_contract_any(TcState* s, int which, cudaStream_t st) {
   return launch_contract_t<CfgSplit128, kBmKL, LOSS>(s, which, 1.0, st);
 }
 
+template <int BM>
+int launch_loss_bm(TcState* s, double beta, cudaStream_t st) {
+  if (s->Rp == 64) {
+    if (!s->split) return launch_contract_t<CfgFast64, BM, true>(s, 1, beta, st);
+    if (s->TN == 64) return launch_contract_t<CfgSplit64N, BM, true>(s, 1, beta, st);
+    return launch_contract_t<CfgSplit64, BM, true>(s, 1, beta, st);
+  }
+  if (!s->split) return launch_contract_t<CfgFast128, BM, true>(s, 1, beta, st);
+  return launch_contract_t<CfgSplit128, BM, true>(s, 1, beta, st);
+}
+
 // beta != 1 (and != 2): two-output kernel on the hi halves of the operand copies
 int launch_contract_two(TcState* s, int which, double beta, cudaStream_t st) {
   if (!s->part2) NMF_CUDA_CHECK(cudaMalloc(&s->part2, (size_t)s->part_floats * 4));
@@ -1275,9 +1360,23 @@ int tc_loss(TcState* s, const float* W, const float* H, double beta, double* los
   int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
   // S = H W^T over the H-update decomposition (row blocks of H, tiles of W), no second GEMM
-  int grid = launch_contract_any<true>(s, 1, st);
+  if (beta == 1.0) {
+    int grid = launch_loss_bm<kBmKL>(s, beta, st);
+    if (grid <= 0) return 2;
+    tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
+    NMF_LAUNCH_CHECK();
+    return 0;
+  }
+  if (s->vbeta_for != beta) {      // V-only term of this beta, once per (target, beta)
+    v_beta_term_kernel<<<1024, 256, 0, st>>>(s->Vsrc, s->N, s->C, s->ldv, (float)beta, s->vbeta_part);
+    NMF_LAUNCH_CHECK();
+    sum_blocks_kernel<<<1, 256, 0, st>>>(s->vbeta_part, 1024, s->vbeta);
+    NMF_LAUNCH_CHECK();
+    s->vbeta_for = beta;
+  }
+  int grid = beta == 0.0 ? launch_loss_bm<kBmIS>(s, beta, st) : launch_loss_bm<kBmGen>(s, beta, st);
   if (grid <= 0) return 2;
-  tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
+  tc_loss_final_beta_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vbeta, beta, (double)s->N * (double)s->C, loss_dev);
   NMF_LAUNCH_CHECK();
   return 0;
 }

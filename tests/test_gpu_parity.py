@@ -298,3 +298,19 @@ def test_tc_two_output_fit_matches_reference_golden(name):
     for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
         ok, err = _close(got, want, 2e-3, 1e-5)           # 20 iterations, fp16 ratio tiles, single-rounded factors
         assert ok, f"{name} {nm}: scaled err {err:.3e}"
+
+
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1.5, 3])
+@pytest.mark.parametrize("precision", ["f16", "f16_split"])
+def test_tc_loss_other_betas_match_oracle(beta, precision):
+    torch.manual_seed(22)
+    N, C, R = 777, 515, 48
+    V = (torch.rand(N, C) * 3 + 0.02).bfloat16().float()
+    W0 = torch.rand(C, R) + 0.01; H0 = torch.rand(N, R) + 0.01
+    from torchnmf_b200.engine import CudaNmfEngine
+    eng = CudaNmfEngine(V.cuda(), W0.cuda(), H0.cuda(), precision)
+    assert eng.precision_for(beta) == "f16"
+    want = float(orc.beta_div(orc.nmf_reconstruct(H0, W0).double(), V.double(), beta))
+    got = eng.loss(beta)
+    eng.close()
+    assert math.isclose(got, want, rel_tol=3e-4), (beta, got, want)
