@@ -32,7 +32,6 @@ namespace nmfb200 {
 namespace {
 
 constexpr int kTileM = 128;          // rows of the row factor per work item (= TMEM lanes)
-constexpr int kThreads = 512;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0;        // S/P stages: columns [TN i, TN i + TN); O accumulator follows at NS * TN
 
@@ -40,9 +39,12 @@ constexpr uint32_t kColS = 0;        // S/P stages: columns [TN i, TN i + TN); O
 //   RP    padded rank (64 or 128);  SPLIT  hi|lo fp16 factors (KW = 2 RP operand columns)
 //   TN    tile width in columns of V (64 or 128): narrower tiles = deeper rings in the same shared memory
 //   NF / NG / NV  F blocks, G-tile ring, V-tile ring;  NS  S/P accumulator stages in TMEM;  AHEAD  S lookahead
-template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int AHEAD_>
+//   NRW   ratio warpgroups (tile t is processed by warpgroup t % NRW)
+template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int AHEAD_, int NRW_ = 2>
 struct Cfg {
-  static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, AHEAD = AHEAD_;
+  static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, AHEAD = AHEAD_, NRW = NRW_;
+  // warps 0-3: TMA (V) / MMA / TMA (F,G) / spare; then 4 NRW ratio warps; then 4 epilogue warps
+  static constexpr int kThreads = 128 + 128 * NRW_ + 128;
   static constexpr bool SPLIT = SPLIT_;
   static constexpr int KW = RP_ * (SPLIT_ ? 2 : 1);
 };
@@ -61,6 +63,7 @@ struct TcKernelParams {
   double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
   const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
   int pf_dist;                // L2 prefetch distance of the V stream in tiles (0 = off)
+  int skip_g;                 // tuning experiment: skip the G-tile loads after the first ring fill (results invalid)
   long long* trace;           // tuning aid: per-tile event timestamps of CTA 0 ([tile][12]), or nullptr
 };
 
@@ -82,7 +85,7 @@ struct SmemLayout {
   static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 2 * NS + 2;
   static constexpr int kTmemPtr = kBar + 8 * kNumBars;
   static constexpr int kLossSlots = kTmemPtr + 16;
-  static constexpr int kTotal = kLossSlots + 16 * 8;
+  static constexpr int kTotal = kLossSlots + 16 * 16;
 };
 
 // BM selects the phi stage (nmf.py:61-74): 0 = beta 1 (one centred ratio tile, one accumulator); otherwise two tiles
@@ -91,11 +94,13 @@ struct SmemLayout {
 enum : int { kBmKL = 0, kBmIS = 1, kBm05 = 2, kBm15 = 3, kBmGen = 4 };
 
 template <class C, int BM, bool LOSS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(C::kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
   constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS, AHEAD = C::AHEAD;
   constexpr bool SPLIT = C::SPLIT;
+  constexpr int NRW = C::NRW;
+  constexpr int kEpiWarp0 = 4 + 4 * NRW;          // first epilogue warp
   constexpr bool TWO = BM != kBmKL && !LOSS;     // LOSS kernels only need S, whatever the beta
   // TMEM columns.  one-output: S/P stages [0, NS TN) | O [NS TN, NS TN + KW).
   //               two-output: S/Pn stages [0, 256) | Pp stages [256, 384) | O_num [384, 448) | O_den [448, 512)
@@ -204,6 +209,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           const uint32_t s = t % NG, ph = (t / NG) & 1;
           ptx::mbar_wait(BAR(B_GEMPTY + s), ph ^ 1);
           TC_TRACE(t, 8);
+          if (p.skip_g && t >= (uint32_t)NG) { ptx::mbar_arrive(BAR(B_GFULL + s)); continue; }
           ptx::mbar_expect_tx(BAR(B_GFULL + s), L::kGBytes);
           for (int kb = 0; kb < KW / 64; ++kb)
             ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (TN * 128), kb * 64, j * TN);
@@ -319,9 +325,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < kEpiWarp0) {
     // =========================== ratio warpgroups =======================
-    const int g = (warp - 4) >> 2;             // 0: even tiles, 1: odd tiles
+    const int g = (warp - 4) >> 2;             // this warpgroup handles tiles t with t % NRW == g
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -350,7 +356,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       const bool row_ok = (item % p.row_blocks) * kTileM + row < p.Mr;
       for (int j = 0; j < n; ++j) {
         const uint32_t tt = t + j;
-        if ((int)(tt & 1) != g) continue;
+        if ((int)(tt % NRW) != g) continue;
         const uint32_t s = tt % NV, st = tt % NS;
         if (q == 0 && lane == 0) TC_TRACE(tt, 2);
         ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);              // V tile landed (TMA -> this thread)
@@ -472,7 +478,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       }
       if (lane == 0) { loss_slots[2 * (warp - 4)] = accA; loss_slots[2 * (warp - 4) + 1] = accB; }
     }
-  } else if (warp >= 12 && !LOSS) {
+  } else if (warp >= kEpiWarp0 && !LOSS) {
     // =========================== epilogue warpgroup =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -569,7 +575,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   if (warp == 1) ptx::tmem_dealloc(tmem, kTmemCols);
   if (LOSS && threadIdx.x == 96) {          // fixed-order sum of the 8 ratio warps
     double a = 0.0, b = 0.0;
-    for (int w = 0; w < 8; ++w) { a += loss_slots[2 * w]; b += loss_slots[2 * w + 1]; }
+    for (int w = 0; w < 4 * NRW; ++w) { a += loss_slots[2 * w]; b += loss_slots[2 * w + 1]; }
     p.loss_part[2 * blockIdx.x] = a;
     p.loss_part[2 * blockIdx.x + 1] = b;
   }
@@ -1222,13 +1228,14 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   p.kappa = s->kappa;
   p.trace = s->trace;
   p.pf_dist = s->pf_dist;
+  p.skip_g = getenv("NMFB200_TC_SKIPG") ? 1 : 0;
   if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 12 * sizeof(long long), st);
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
   if (which == 0)
-    kern<<<grid, kThreads, smem, st>>>(s->tmWf, s->tmHg, s->tmVt, p);
+    kern<<<grid, C::kThreads, smem, st>>>(s->tmWf, s->tmHg, s->tmVt, p);
   else
-    kern<<<grid, kThreads, smem, st>>>(s->tmHf, s->tmWg, s->tmV, p);
+    kern<<<grid, C::kThreads, smem, st>>>(s->tmHf, s->tmWg, s->tmV, p);
   NMF_LAUNCH_CHECK();
   return grid;
 }
@@ -1242,10 +1249,16 @@ using CfgSplit64N = Cfg<64, true, 64, 1, 6, 6, 4, 2>;       // (variant 1) 64-co
 using CfgFast128 = Cfg<128, false, 128, 1, 3, 3, 3, 1>;     // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
 using CfgSplit128 = Cfg<128, true, 64, 1, 3, 4, 4, 1>;      // F 64 | G 3x32 | V 4x16 KB     ; TMEM 4x64 + 256
 
+using CfgFast64R3 = Cfg<64, false, 128, 2, 4, 4, 3, 2, 3>;    // three ratio warpgroups (one per S stage), 640 threads
+using CfgSplit64R3 = Cfg<64, true, 128, 1, 3, 3, 3, 1, 3>;
 using CfgTwo64 = Cfg<64, false, 128, 2, 3, 4, 2, 1>;        // beta != 1: F 2x16 | G 3x16 | V 4x32 KB ; TMEM 2x128 + 128 + 2x64
 
 template <bool LOSS>
 int launch_contract_any(TcState* s, int which, cudaStream_t st) {
+  if (s->Rp == 64 && !LOSS && s->variant == 3) {
+    if (!s->split) return launch_contract_t<CfgFast64R3, kBmKL, LOSS>(s, which, 1.0, st);
+    return launch_contract_t<CfgSplit64R3, kBmKL, LOSS>(s, which, 1.0, st);
+  }
   if (s->Rp == 64) {
     if (!s->split) return launch_contract_t<CfgFast64, kBmKL, LOSS>(s, which, 1.0, st);
     if (s->TN == 64) return launch_contract_t<CfgSplit64N, kBmKL, LOSS>(s, which, 1.0, st);
