@@ -46,6 +46,24 @@ def load_peaks():
     return dict(hbm=6650.0, tc=1590.0, tc_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic(precision, cfg_name):
+    """dram read+write bytes per launch of the fused contraction kernel from the committed ncu capture
+    (profiles/r1_ncu_tc_contract_<precision>.txt, taken at cfg2); None when no capture matches."""
+    if cfg_name != "cfg2":
+        return None
+    path = os.path.join(ROOT, "profiles", f"r1_ncu_tc_contract_{precision}.txt")
+    try:
+        tot = 0.0
+        for ln in open(path):
+            ln = ln.strip()
+            if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
+                val, unit = ln.split("=")[1].split()[:2]
+                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def make_inputs(N, C, R, seed):
     torch.manual_seed(seed)
     V = torch.rand(N, C).bfloat16().float()
@@ -332,7 +350,7 @@ def main():
     which_dom = max(times, key=times.get)
     ach_tf = flops_launch / t_dom / 1e12
     roof = {"bound": "tensor", "achieved": ach_tf, "peak": peaks["tc"], "unit": "TFLOP/s", "frac": ach_tf / peaks["tc"],
-            "traffic": None, "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16 burst (f16 has the same tensor peak)",
+            "traffic": ncu_traffic(precision, a.config), "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16 burst (f16 has the same tensor peak)",
             "kernel": f"fused {which_dom}-update contraction ({precision})", "kernel_ms": t_dom * 1e3,
             "kernel_ms_w": times["w"] * 1e3, "kernel_ms_h": times["h"] * 1e3,
             "algorithmic_flops_per_launch": flops_launch,
