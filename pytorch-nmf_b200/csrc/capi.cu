@@ -281,6 +281,7 @@ int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced, double
   CTX_GUARD(ctx, 0);
   if (!W || !reduced) return fail(NMFB200_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta)) return tc_w_apply(ctx->tc, W, reduced, beta, gamma, l1_reg, l2_reg, st);
   const int64_t CR = ctx->C * ctx->R;
   ApplyArgs a{};
   a.param = W; a.numel = CR; a.R = (int)ctx->R; a.inner = 1; a.rowlen = ctx->R;

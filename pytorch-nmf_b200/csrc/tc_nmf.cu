@@ -1035,6 +1035,7 @@ struct TcState {
   long long* trace = nullptr;       // NMFB200_TC_TRACE=<file>: event timestamps of CTA 0 (tuning aid)
   const char* trace_path = nullptr;
   float* kappa = nullptr;           // device scalar
+  float* zero = nullptr;            // device scalar 0 (kappa of an already complete numerator)
 };
 
 bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
@@ -1046,7 +1047,7 @@ void tc_destroy(TcState* s) {
   cudaSetDevice(s->device);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
-  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->trace);
+  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->zero); cudaFree(s->trace);
   delete s;
 }
 
@@ -1062,7 +1063,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
   if (const char* e = getenv("NMFB200_TC_TRACE")) {
     s->trace_path = e;
-    cudaMalloc(&s->trace, 256 * 12 * sizeof(long long));
+    if (cudaMalloc(&s->trace, 256 * 12 * sizeof(long long)) != cudaSuccess) s->trace = nullptr;
   }
   s->ldc = round_up(C, 8);
   s->ldn = round_up(N, 8);
@@ -1093,6 +1094,8 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->vconst, 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->num_sms * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&s->zero, sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(s->zero, 0, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->vbeta, sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->vbeta_part, 1024 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(s->kappa, 0, sizeof(float));
@@ -1150,8 +1153,10 @@ namespace {
 
 // ratio stage (apply != 0) or plain re-scan (apply == 0) of one factor, then rebuild its fp16 operand copy,
 // column sums and the exponents that depend on it: two launches.
+// `reduced` != nullptr: the sharded path -- numerator (and KL denominator / raw denominator) come from the all-reduced
+// buffer [rows*R num | R colsum or rows*R den] instead of this rank's chunked partials.
 int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double beta, double gamma,
-                     double l1, double l2, cudaStream_t st) {
+                     double l1, double l2, cudaStream_t st, const float* reduced = nullptr) {
   const int64_t rows = which == 0 ? s->C : s->N;
   int rpb = (int)round_up(ceil_div(rows, 1024), 4);
   if (rpb < 64) rpb = 64;
@@ -1164,8 +1169,13 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * s->Rp; a.Rp = s->Rp;
   a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
   a.den = (apply && beta != 1.0) ? s->part2 : nullptr;
+  if (reduced) {
+    a.num = reduced; a.nchunks = 1; a.chunk_stride = 0; a.Rp = (int)s->R;
+    a.kl_den = reduced + rows * s->R;
+    a.den = beta != 1.0 ? reduced + rows * s->R : nullptr;
+  }
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
-  a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = s->kappa;
+  a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = reduced ? s->zero : s->kappa;
   if ((s->R & 3) == 0)
     tc_apply_vec4_kernel<<<blocks, 256, 0, st>>>(a);
   else
@@ -1207,11 +1217,11 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   using L = SmemLayout<C::KW, C::TN, C::NF, C::NG, C::NV, C::NS>;
   static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
   auto kern = tc_contract_kernel<C, BM, LOSS>;
-  static bool attr_set = false;
+  static unsigned long long attr_set_mask = 0;      // per device (one bit each): the attribute is per-device state
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
-  if (!attr_set) {
+  if (!((attr_set_mask >> (s->device & 63)) & 1ull)) {
     NMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set_mask |= 1ull << (s->device & 63);
   }
   if (C::TN != s->TN || C::RP != s->Rp) { set_error("internal: kernel configuration does not match the plan"); return -1; }
   TcKernelParams p{};
@@ -1330,6 +1340,16 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
   add_rowvec_kernel<<<(unsigned)ceil_div(CR, 256), 256, 0, st>>>(partial, CR, (int)s->R, s->colsum + s->R, s->kappa);
   NMF_LAUNCH_CHECK();
   return 0;
+}
+
+// Sharded W update, second half: nmf.py:78-92 on the all-reduced buffer with the tensor-core path's own ratio-stage
+// kernels, which also rebuild W16 / colsum(W) / exponents (no separate resync pass).
+int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double gamma, double l1, double l2,
+               cudaStream_t st) {
+  if (!s->has_target) { set_error("tensor-core path: set_target has not been called"); return 3; }
+  int rc = apply_and_finish(s, 0, W, true, nullptr, beta, gamma, l1, l2, st, reduced);
+  if (rc == 0) s->dirty_w = false;
+  return rc;
 }
 
 // debugging aid: report (and clear) a recorded mbarrier wait abort; synchronises the stream

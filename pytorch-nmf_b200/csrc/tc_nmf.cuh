@@ -21,6 +21,8 @@ int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma,
 int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
                 cudaStream_t st);
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st);
+int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double gamma, double l1, double l2,
+               cudaStream_t st);
 int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st);
 // debugging / health: report (and clear) a recorded mbarrier wait abort; synchronises the stream
 int tc_check_wait_abort(cudaStream_t st);
