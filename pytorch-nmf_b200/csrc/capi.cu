@@ -12,6 +12,7 @@ static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_counter() { return g_launches.load(); }
 }  // namespace nmfb200
 
 using namespace nmfb200;
@@ -240,6 +241,21 @@ int nmfb200_nmf_update_h(nmfb200_ctx* ctx, const float* W, float* H, double beta
   rc = apply_update(a, st);
   if (rc) return rc;
   if (ctx->tc) tc_mark_dirty(ctx->tc, false, true);
+  return 0;
+}
+
+int nmfb200_nmf_iterate(nmfb200_ctx* ctx, float* W, float* H, double beta, double gamma, double l1_reg,
+                        double l2_reg, int n_iter, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || n_iter < 0) return fail(NMFB200_ERR_INVALID, "bad argument");
+  if (use_tc(ctx, beta)) return tc_iterate(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, n_iter, (cudaStream_t)stream);
+  for (int i = 0; i < n_iter; ++i) {
+    int rc = nmfb200_nmf_update_w(ctx, W, H, beta, gamma, l1_reg, l2_reg, stream);
+    if (rc) return rc;
+    rc = nmfb200_nmf_update_h(ctx, W, H, beta, gamma, l1_reg, l2_reg, stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

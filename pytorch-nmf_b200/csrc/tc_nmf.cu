@@ -1028,6 +1028,14 @@ struct TcState {
   CUtensorMap tmWg, tmHg;           // factors as the column factor G: box 64 x TN
   Plan plan_w, plan_h;
   uint32_t upd[2] = {0, 0};         // per-factor update counter (selects the absmax slot)
+  // one MU iteration (W update + H update) captured as a CUDA graph, per absmax-slot parity pair
+  cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};
+  int gkernels = 0;                 // kernels per captured iteration (for the launch counter)
+  const float* gW = nullptr; const float* gH = nullptr;
+  double gargs[4] = {0, 0, 0, 0};   // beta, gamma, l1, l2 the graphs were captured with
+  bool gwarm = false;               // one eager iteration has run with these arguments
+  cudaStream_t gstream = nullptr;   // capture / replay stream (the caller's may be the legacy default stream, which cannot capture)
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   bool dirty_w = true, dirty_h = true, has_target = false;
   int center = 1;
   int pf_dist = 0;
@@ -1042,9 +1050,18 @@ bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
   return R >= 1 && R <= 128 && N >= 1 && C >= 1 && N < (1ll << 31) && C < (1ll << 31);
 }
 
+static void drop_graphs(TcState* s) {
+  for (auto& g : s->gexec) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+  s->gwarm = false;
+}
+
 void tc_destroy(TcState* s) {
   if (!s) return;
   cudaSetDevice(s->device);
+  drop_graphs(s);
+  if (s->gstream) cudaStreamDestroy(s->gstream);
+  if (s->gev_in) cudaEventDestroy(s->gev_in);
+  if (s->gev_out) cudaEventDestroy(s->gev_out);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
   cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->zero); cudaFree(s->trace);
@@ -1140,6 +1157,7 @@ int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_d
   NMF_LAUNCH_CHECK();
   s->has_target = true;
   s->Vsrc = V; s->ldv = ldv; s->vbeta_for = 1.0;
+  drop_graphs(s);
   s->dirty_w = s->dirty_h = true;      // exps[3] depends on sum(V)
   return 0;
 }
@@ -1323,6 +1341,68 @@ int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma,
   rc = launch_contract(s, 1, beta, st);
   if (rc) return rc;
   return apply_and_finish(s, 1, H, true, &s->plan_h, beta, gamma, l1, l2, st);
+}
+
+int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double l1, double l2, int n_iter,
+               cudaStream_t st) {
+  if (n_iter <= 0) return 0;
+  if (s->gW != W || s->gH != H || s->gargs[0] != beta || s->gargs[1] != gamma || s->gargs[2] != l1 || s->gargs[3] != l2) {
+    drop_graphs(s);
+    s->gW = W; s->gH = H; s->gargs[0] = beta; s->gargs[1] = gamma; s->gargs[2] = l1; s->gargs[3] = l2;
+  }
+  // CUDA-graph replay of the iteration is opt-in (NMFB200_GRAPH=1): measured no gain at cfg2 -- the stream is never
+  // launch-bound (profiles/README.md) -- so the default keeps plain stream-ordered launches.
+  const bool use_graph = getenv("NMFB200_GRAPH") != nullptr && s->trace == nullptr;
+  cudaStream_t user = st;
+  if (use_graph) {
+    // run on an engine-owned stream, fenced against the caller's stream with events
+    if (!s->gstream) {
+      NMF_CUDA_CHECK(cudaStreamCreateWithFlags(&s->gstream, cudaStreamNonBlocking));
+      NMF_CUDA_CHECK(cudaEventCreateWithFlags(&s->gev_in, cudaEventDisableTiming));
+      NMF_CUDA_CHECK(cudaEventCreateWithFlags(&s->gev_out, cudaEventDisableTiming));
+    }
+    NMF_CUDA_CHECK(cudaEventRecord(s->gev_in, user));
+    NMF_CUDA_CHECK(cudaStreamWaitEvent(s->gstream, s->gev_in, 0));
+    st = s->gstream;
+  }
+  int rc = ensure_synced(s, W, H, beta, st);        // graphs assume clean operand copies
+  if (rc) return rc;
+  if (beta != 1.0 && !s->part2) NMF_CUDA_CHECK(cudaMalloc(&s->part2, (size_t)s->part_floats * 4));
+  for (int i = 0; i < n_iter; ++i) {
+    const int key = (int)((s->upd[0] & 1u) * 2u + (s->upd[1] & 1u));
+    if (use_graph && s->gwarm && s->gexec[key]) {
+      NMF_CUDA_CHECK(cudaGraphLaunch(s->gexec[key], st));
+      s->upd[0]++; s->upd[1]++;
+      count_launch(s->gkernels);
+      continue;
+    }
+    const bool capture = use_graph && s->gwarm;      // the first iteration runs eagerly (lazy module loads, attributes)
+    cudaGraph_t graph = nullptr;
+    const int64_t before = launch_counter();
+    if (capture) NMF_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = tc_update_w(s, W, H, beta, gamma, l1, l2, st);
+    if (rc == 0) rc = tc_update_h(s, W, H, beta, gamma, l1, l2, st);
+    if (capture) {
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc == 0 && e != cudaSuccess) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); rc = 2; }
+      if (rc == 0) {
+        e = cudaGraphInstantiate(&s->gexec[key], graph, 0);
+        if (e != cudaSuccess) { set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); rc = 2; }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      if (rc) { drop_graphs(s); return rc; }
+      s->gkernels = (int)(launch_counter() - before);
+      NMF_CUDA_CHECK(cudaGraphLaunch(s->gexec[key], st));      // capture records, it does not execute
+    } else {
+      if (rc) return rc;
+      s->gwarm = true;
+    }
+  }
+  if (use_graph) {
+    NMF_CUDA_CHECK(cudaEventRecord(s->gev_out, s->gstream));
+    NMF_CUDA_CHECK(cudaStreamWaitEvent(user, s->gev_out, 0));
+  }
+  return 0;
 }
 
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st) {

@@ -20,6 +20,8 @@ int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma,
                 cudaStream_t st);
 int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
                 cudaStream_t st);
+int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double l1, double l2, int n_iter,
+               cudaStream_t st);
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st);
 int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double gamma, double l1, double l2,
                cudaStream_t st);

@@ -139,6 +139,11 @@ class CudaNmfEngine(_CudaEngine):
         _capi.check(self._lib.nmfb200_nmf_update_h(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
                                                    l2_reg, _stream(self.device)))
 
+    def iterate(self, n_iter, beta, gamma, l1_reg, l2_reg):
+        """n_iter x (update_w; update_h) in one call (CUDA-graph replay on the tensor-core path)."""
+        _capi.check(self._lib.nmfb200_nmf_iterate(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg, l2_reg,
+                                                  int(n_iter), _stream(self.device)))
+
     def loss_tensor(self, beta):
         _capi.check(self._lib.nmfb200_nmf_loss(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
                                                _stream(self.device)))

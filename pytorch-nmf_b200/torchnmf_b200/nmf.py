@@ -181,8 +181,21 @@ class BaseComponent(torch.nn.Module):
             train_w, train_h = W.requires_grad, H.requires_grad
             bar = _tqdm(total=max_iter, disable=not verbose) if _tqdm is not None else _NullBar()
             n_iter = -1
+            batched = train_w and train_h and group is None and hasattr(eng, "iterate")
             with bar as pbar:
-                for n_iter in range(max_iter):                                             # nmf.py:366
+                while batched and n_iter + 1 < max_iter:
+                    # both factors trainable: run the iterations up to the next loss evaluation in one engine call
+                    k = min(10 - ((n_iter + 1) % 10), max_iter - (n_iter + 1))
+                    eng.iterate(k, beta, gamma, l1_reg, l2_reg)                            # nmf.py:366-391, k times
+                    n_iter += k
+                    if n_iter % 10 == 9:                                                   # nmf.py:393
+                        loss = fit_loss()
+                        pbar.set_postfix(loss=loss)
+                        pbar.update(10)
+                        if (previous_loss - loss) / loss_init < tol:                       # nmf.py:405
+                            break
+                        previous_loss = loss
+                for n_iter in (range(max_iter) if not batched else ()):                    # nmf.py:366
                     if train_w:
                         eng.update_w(beta, gamma, l1_reg, l2_reg)                          # nmf.py:367-378
                     if train_h:
