@@ -159,7 +159,7 @@ int nmfb200_precision_for_beta(const nmfb200_ctx* ctx, double beta) {
   if (!ctx) return -100;
   if (ctx->kind != 0 || !use_tc(ctx, beta)) return NMFB200_PREC_F32;
   // beta != 1 kernels read only the hi halves of the operand copies
-  return beta == 1.0 ? ctx->precision : NMFB200_PREC_F16;
+  return (beta == 1.0 || beta == 2.0) ? ctx->precision : NMFB200_PREC_F16;
 }
 
 int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* stream) {
@@ -281,7 +281,7 @@ int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, doub
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H || !partial) return fail(NMFB200_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(ctx, beta)) return tc_w_partial(ctx->tc, W, H, beta, partial, st);
+  if (use_tc(ctx, beta) && tc_supports_partial(ctx->tc, beta)) return tc_w_partial(ctx->tc, W, H, beta, partial, st);
   int rc = simt_contract_w(ctx, W, H, beta, st);
   if (rc) return rc;
   const int64_t CR = ctx->C * ctx->R;

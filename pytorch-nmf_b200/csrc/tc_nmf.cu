@@ -91,7 +91,10 @@ struct SmemLayout {
 // BM selects the phi stage (nmf.py:61-74): 0 = beta 1 (one centred ratio tile, one accumulator); otherwise two tiles
 // Pn = V x^(beta-2), Pp = x^(beta-1) and two accumulators (numerator, denominator): 1 = beta 0, 2 = beta 0.5,
 // 3 = beta 1.5, 4 = any other beta (lg2/ex2).
-enum : int { kBmKL = 0, kBmIS = 1, kBm05 = 2, kBm15 = 3, kBmGen = 4 };
+// 5 = beta 2: the tile is the scale-matched residual V - kappa WH (signed, no MUFU work); numerator = O + kappa W (H^T H)
+// is rebuilt in fp32 by the ratio stage, the same trick as the kappa centring of beta 1 (all-positive sums would inherit the
+// tensor cores' truncation bias).
+enum : int { kBmKL = 0, kBmIS = 1, kBm05 = 2, kBm15 = 3, kBmGen = 4, kBmEU = 5 };
 
 template <class C, int BM, bool LOSS>
 __global__ void __launch_bounds__(C::kThreads, 1)
@@ -101,7 +104,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   constexpr bool SPLIT = C::SPLIT;
   constexpr int NRW = C::NRW;
   constexpr int kEpiWarp0 = 4 + 4 * NRW;          // first epilogue warp
-  constexpr bool TWO = BM != kBmKL && !LOSS;     // LOSS kernels only need S, whatever the beta
+  constexpr bool TWO = BM != kBmKL && BM != kBmEU && !LOSS;     // LOSS kernels only need S, whatever the beta
+  constexpr bool EU = BM == kBmEU;
   // TMEM columns.  one-output: S/P stages [0, NS TN) | O [NS TN, NS TN + KW).
   //               two-output: S/Pn stages [0, 256) | Pp stages [256, 384) | O_num [384, 448) | O_den [448, 512)
   constexpr uint32_t kColPp = NS * TN;
@@ -344,7 +348,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     // (measured: -4.7e-5 relative on this all-positive sum, profiles/README.md), a one-signed bias that the
     // scale-free direction (W a, H / a) of KL-NMF integrates over iterations; the centred sum is signed and
     // small, and its fp16 rounding error is relative to |P - kappa| instead of |P|.
-    const float negpc = (LOSS || TWO) ? 0.f : -(*p.kappa) * exp2f((float)ep);
+    const float negpc = (LOSS || TWO || EU) ? 0.f : -(*p.kappa) * exp2f((float)ep);
+    // beta 2: P~ = (V - WH) 2^pe = v~ cv - s~ cs   (pe = exps[4], from mean(V)); loss: true scale (pe = 0)
+    const float eu_cv = EU ? exp2f((float)((LOSS ? 0 : p.exps[4]) - ev)) : 0.f;
+    // update: the tile is V - kappa WH with kappa = sum(V) / sum(WH) (the scale-matched residual; kappa -> 1 as the fit
+    // converges), so that far from convergence (WH >> V) the numerator is not a small difference of large sums
+    const float eu_cs = EU ? exp2f((float)((LOSS ? 0 : p.exps[4]) - ea - eb)) * (LOSS ? 1.f : *p.kappa) : 0.f;
     double accA = 0.0, accB = 0.0;
     uint32_t t = 0;
     const float vinv = exp2f(-(float)ev);
@@ -380,7 +389,18 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           }
           ptx::tc_wait_ld();
           const uint32_t* vw = reinterpret_cast<const uint32_t*>(vv);
-          if (LOSS && BM == kBmKL) {
+          if (LOSS && EU) {
+            float la = 0.f;                        // metrics.py:39: 0.5 sum (WH - V)^2 (zero-filled edges contribute 0)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+              const float d0 = fmaf(vf.x, eu_cv, -__uint_as_float(sreg[2 * i]) * eu_cs);
+              const float d1 = fmaf(vf.y, eu_cv, -__uint_as_float(sreg[2 * i + 1]) * eu_cs);
+              la = fmaf(d0, d0, la);
+              la = fmaf(d1, d1, la);
+            }
+            accA += (double)la;
+          } else if (LOSS && BM == kBmKL) {
             float la = 0.f, lb = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -421,6 +441,16 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             }
             accA += (double)la;
             accB += (double)lb;
+          } else if (EU) {
+            uint32_t preg[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+              const float p0 = fmaf(vf.x, eu_cv, -__uint_as_float(sreg[2 * i]) * eu_cs);      // nmf.py:62-63: V - WH
+              const float p1 = fmaf(vf.y, eu_cv, -__uint_as_float(sreg[2 * i + 1]) * eu_cs);
+              preg[i] = ptx::pack_f16x2_sat(p0, p1);
+            }
+            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, preg);
           } else if (TWO) {
             uint32_t pn[16], pp[16];
 #pragma unroll
@@ -483,7 +513,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float oscale = exp2f(-(float)(p.exps[p.eg] + p.exps[TWO ? 4 : 3]));      // O = sum (P 2^p) (G 2^eg)
+    const float oscale = exp2f(-(float)(p.exps[p.eg] + p.exps[(TWO || EU) ? 4 : 3]));      // O = sum (P 2^p) (G 2^eg)
     const float oscale2 = TWO ? exp2f(-(float)(p.exps[p.eg] + p.exps[5])) : 0.f;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -777,6 +807,96 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
 }
 
+// beta 2 denominators.  gram_part_kernel: per-slab partial G^T G (R x R, fp32); gram_sum_kernel folds the slabs in
+// fixed order.  tc_apply_eu_kernel: den_raw = F (G^T G) row by row (the reference's relu(S^T G), nmf.py:63,82, since
+// S = F G^T), num = O + den_raw with O = (V - S)-contraction from the tensor cores, then nmf.py:78-92.
+__global__ void __launch_bounds__(256)
+gram_part_kernel(const float* __restrict__ x, int64_t rows, int R, int64_t rows_per_block, float* __restrict__ part) {
+  extern __shared__ float xs[];                 // [32][R]
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  const int nout = R * R;
+  float acc[64];                                // up to 128*128/256 outputs per thread
+#pragma unroll
+  for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+  for (int64_t base = r0; base < r1; base += 32) {
+    const int nr = (int)min((int64_t)32, r1 - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * R; i += 256) xs[i] = x[base * R + i];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+      const int o = threadIdx.x + k * 256;
+      if (o < nout) {
+        const int i = o / R, j = o - i * R;
+        float t = acc[k];
+        for (int rr = 0; rr < nr; ++rr) t = fmaf(xs[rr * R + i], xs[rr * R + j], t);
+        acc[k] = t;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const int o = threadIdx.x + k * 256;
+    if (o < nout) part[(int64_t)blockIdx.x * nout + o] = acc[k];
+  }
+}
+__global__ void __launch_bounds__(256)
+gram_sum_kernel(const float* __restrict__ part, int nb, int nout, float* __restrict__ out) {
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= nout) return;
+  float t = 0.f;
+  for (int b = 0; b < nb; ++b) t += part[(int64_t)b * nout + o];
+  out[o] = t;
+}
+
+// one thread per (row, r); a block stages its rows' old values in shared memory before anything is overwritten
+__global__ void __launch_bounds__(256)
+tc_apply_eu_kernel(TcApplyArgs a, const float* __restrict__ gram) {
+  extern __shared__ float rowbuf[];             // [rows_per_pass][R]
+  __shared__ float sh[256];
+  const int rows_per_pass = 256 / a.R > 0 ? 256 / a.R : 1;
+  const int rl = threadIdx.x / a.R, r = threadIdx.x - rl * a.R;
+  const bool active = rl < rows_per_pass;
+  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
+  const int64_t row1 = min(a.rows, row0 + a.rpb);
+  float cs = 0.f, mx = 0.f;
+  const float kap = *a.kappa;
+  for (int64_t base = row0; base < row1; base += rows_per_pass) {
+    const int64_t row = base + rl;
+    const bool ok = active && row < row1;
+    __syncthreads();
+    float v = 0.f;
+    if (ok) { v = a.param[row * a.R + r]; rowbuf[rl * a.R + r] = v; }
+    __syncthreads();
+    if (ok) {
+      float den = 0.f;                                          // (F G^T G)[row, r] = S^T-contraction, nmf.py:82
+      for (int k = 0; k < a.R; ++k) den = fmaf(rowbuf[rl * a.R + k], gram[k * a.R + r], den);
+      float num = kap * den;                                    // numerator = (V - kappa S) G + kappa S G
+      for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * a.Rp + r];
+      const float neg = fmaxf(num, 0.f) + kEps;                // nmf.py:78
+      float pos = fmaxf(den, 0.f) + kEps;                      // nmf.py:83
+      if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
+      if (a.l2 > 0.f) pos = fmaf(a.l2, v, pos);                 // nmf.py:87-88
+      float mult = neg / pos;                                   // nmf.py:89
+      if (a.gamma != 1.0f) mult = powf(mult, a.gamma);          // nmf.py:90-91 (gamma == 1 for beta 2)
+      v *= mult;                                                // nmf.py:92
+      a.param[row * a.R + r] = v;
+      cs += v;
+      mx = fmaxf(mx, v);
+    }
+  }
+  sh[threadIdx.x] = cs;
+  __syncthreads();
+  if (threadIdx.x < a.R) {
+    float t = 0.f;
+    for (int k = 0; k < rows_per_pass; ++k) t += sh[k * a.R + threadIdx.x];
+    a.cs_part[(int64_t)blockIdx.x * 128 + threadIdx.x] = t;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(a.absmax, __float_as_uint(mx));
+}
+
 // fp32 factor (rows x R) -> fp16 operand copy (rows x KW): [hi(0..Rp) | lo(Rp..2Rp)] scaled by 2^a, a from the
 // max found by tc_apply_kernel; pad columns stay zero (buffer zero-initialised once).  Block 0 additionally
 // finishes the column sums, publishes exps[1 + which] = a, and re-derives kappa = sum(V) / sum(W H^T) =
@@ -913,7 +1033,8 @@ __global__ void tc_loss_final_beta_kernel(const double* __restrict__ part, int n
   double a = 0.0, b = 0.0;
   for (int i = 0; i < nblk; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
   const double ln2 = 0.693147180559945309417;
-  if (beta == 0.0) *out = a - *vb + ln2 * b - cells;
+  if (beta == 2.0) *out = 0.5 * a;
+  else if (beta == 0.0) *out = a - *vb + ln2 * b - cells;
   else *out = (*vb + (beta - 1.0) * b - beta * a) / (beta * (beta - 1.0));
 }
 
@@ -1007,6 +1128,8 @@ struct TcState {
   __half *V16 = nullptr, *Vt16 = nullptr, *W16 = nullptr, *H16 = nullptr;
   float* part = nullptr;
   float* part2 = nullptr;           // denominators of the beta != 1 kernels (allocated on first use)
+  float* gram = nullptr;            // beta 2: G^T G (R x R) and its per-slab partials [256][R*R] (allocated on first use)
+  float* gram_part = nullptr;
   int64_t part_floats = 0;
   float* colsum = nullptr;          // [2][R]  0 = W, 1 = H
   float* cs_part = nullptr;         // [<=1024][128]
@@ -1062,7 +1185,7 @@ void tc_destroy(TcState* s) {
   if (s->gstream) cudaStreamDestroy(s->gstream);
   if (s->gev_in) cudaEventDestroy(s->gev_in);
   if (s->gev_out) cudaEventDestroy(s->gev_out);
-  cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2);
+  cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2); cudaFree(s->gram); cudaFree(s->gram_part);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
   cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->zero); cudaFree(s->trace);
   delete s;
@@ -1141,10 +1264,12 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
 
 bool tc_supports_beta(const TcState* s, double beta) {
   if (beta == 1.0) return true;
-  // beta != 1: two-output kernel (rank <= 64); beta == 2 stays on the fp32 path (its ratio tiles are V and WH themselves)
-  return beta != 2.0 && s->Rp == 64 && s->TN == 128;
+  if (beta == 2.0) return true;    // residual kernel, any configuration
+  // other beta: two-output kernel (rank <= 64)
+  return s->Rp == 64 && s->TN == 128;
 }
 bool tc_supports_loss(const TcState* s, double beta) { return tc_supports_beta(s, beta); }
+bool tc_supports_partial(const TcState* s, double beta) { return beta != 2.0 && tc_supports_beta(s, beta); }
 
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st) {
   set_vexp_kernel<<<1, 32, 0, st>>>(minmax_dev, s->exps);
@@ -1174,7 +1299,8 @@ namespace {
 // `reduced` != nullptr: the sharded path -- numerator (and KL denominator / raw denominator) come from the all-reduced
 // buffer [rows*R num | R colsum or rows*R den] instead of this rank's chunked partials.
 int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double beta, double gamma,
-                     double l1, double l2, cudaStream_t st, const float* reduced = nullptr) {
+                     double l1, double l2, cudaStream_t st, const float* reduced = nullptr,
+                     const float* other = nullptr) {
   const int64_t rows = which == 0 ? s->C : s->N;
   int rpb = (int)round_up(ceil_div(rows, 1024), 4);
   if (rpb < 64) rpb = 64;
@@ -1186,7 +1312,7 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   a.param = param; a.rows = rows; a.R = (int)s->R; a.rpb = rpb;
   a.num = s->part; a.nchunks = pl ? pl->nchunks : 0; a.chunk_stride = rows * s->Rp; a.Rp = s->Rp;
   a.kl_den = s->colsum + (1 - which) * s->R;     // W update divides by colsum(H), H update by colsum(W)
-  a.den = (apply && beta != 1.0) ? s->part2 : nullptr;
+  a.den = (apply && beta != 1.0 && beta != 2.0) ? s->part2 : nullptr;
   if (reduced) {
     a.num = reduced; a.nchunks = 1; a.chunk_stride = 0; a.Rp = (int)s->R;
     a.kl_den = reduced + rows * s->R;
@@ -1194,10 +1320,29 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   }
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = reduced ? s->zero : s->kappa;
-  if ((s->R & 3) == 0)
+  if (apply && beta == 2.0 && !reduced) {
+    // den_raw = F (G^T G): Gram matrix of the other factor (fp32, fixed-order two-level sum), then the EU ratio stage
+    if (!other) { set_error("internal: beta 2 update without the other factor"); return 1; }
+    const int R = (int)s->R, nout = R * R;
+    if (!s->gram) {
+      NMF_CUDA_CHECK(cudaMalloc(&s->gram, (size_t)nout * 4));
+      NMF_CUDA_CHECK(cudaMalloc(&s->gram_part, (size_t)256 * nout * 4));
+    }
+    const int64_t orows = which == 0 ? s->N : s->C;
+    int64_t rpbg = round_up(ceil_div(orows, 256), 32);
+    const int nb = (int)ceil_div(orows, rpbg);
+    gram_part_kernel<<<nb, 256, 32 * R * sizeof(float), st>>>(other, orows, R, rpbg, s->gram_part);
+    NMF_LAUNCH_CHECK();
+    gram_sum_kernel<<<(unsigned)ceil_div(nout, 256), 256, 0, st>>>(s->gram_part, nb, nout, s->gram);
+    NMF_LAUNCH_CHECK();
+    a.den = nullptr;
+    const int rows_per_pass = 256 / R > 0 ? 256 / R : 1;
+    tc_apply_eu_kernel<<<blocks, 256, rows_per_pass * R * sizeof(float), st>>>(a, s->gram);
+  } else if ((s->R & 3) == 0) {
     tc_apply_vec4_kernel<<<blocks, 256, 0, st>>>(a);
-  else
+  } else {
     tc_apply_kernel<<<blocks, 256, 0, st>>>(a);
+  }
   NMF_LAUNCH_CHECK();
   __half* out = which == 0 ? s->W16 : s->H16;
   const unsigned grid = (unsigned)ceil_div((s->R & 7) == 0 ? rows * (s->R >> 3) : rows * s->R, 256);
@@ -1281,19 +1426,20 @@ using CfgFast64R3 = Cfg<64, false, 128, 2, 4, 4, 3, 2, 3>;    // three ratio war
 using CfgSplit64R3 = Cfg<64, true, 128, 1, 3, 3, 3, 1, 3>;
 using CfgTwo64 = Cfg<64, false, 128, 2, 3, 4, 2, 1>;        // beta != 1: F 2x16 | G 3x16 | V 4x32 KB ; TMEM 2x128 + 128 + 2x64
 
-template <bool LOSS>
-int launch_contract_any(TcState* s, int which, cudaStream_t st) {
-  if (s->Rp == 64 && !LOSS && s->variant == 3) {
-    if (!s->split) return launch_contract_t<CfgFast64R3, kBmKL, LOSS>(s, which, 1.0, st);
-    return launch_contract_t<CfgSplit64R3, kBmKL, LOSS>(s, which, 1.0, st);
+// one-output kernels (beta 1: BM = kBmKL, beta 2: BM = kBmEU) over the configuration of this context
+template <int BM>
+int launch_contract_one(TcState* s, int which, double beta, cudaStream_t st) {
+  if (s->Rp == 64 && BM == kBmKL && s->variant == 3) {
+    if (!s->split) return launch_contract_t<CfgFast64R3, BM, false>(s, which, beta, st);
+    return launch_contract_t<CfgSplit64R3, BM, false>(s, which, beta, st);
   }
   if (s->Rp == 64) {
-    if (!s->split) return launch_contract_t<CfgFast64, kBmKL, LOSS>(s, which, 1.0, st);
-    if (s->TN == 64) return launch_contract_t<CfgSplit64N, kBmKL, LOSS>(s, which, 1.0, st);
-    return launch_contract_t<CfgSplit64, kBmKL, LOSS>(s, which, 1.0, st);
+    if (!s->split) return launch_contract_t<CfgFast64, BM, false>(s, which, beta, st);
+    if (s->TN == 64) return launch_contract_t<CfgSplit64N, BM, false>(s, which, beta, st);
+    return launch_contract_t<CfgSplit64, BM, false>(s, which, beta, st);
   }
-  if (!s->split) return launch_contract_t<CfgFast128, kBmKL, LOSS>(s, which, 1.0, st);
-  return launch_contract_t<CfgSplit128, kBmKL, LOSS>(s, which, 1.0, st);
+  if (!s->split) return launch_contract_t<CfgFast128, BM, false>(s, which, beta, st);
+  return launch_contract_t<CfgSplit128, BM, false>(s, which, beta, st);
 }
 
 template <int BM>
@@ -1319,8 +1465,9 @@ int launch_contract_two(TcState* s, int which, double beta, cudaStream_t st) {
 }
 
 int launch_contract(TcState* s, int which, double beta, cudaStream_t st) {
+  if (beta == 2.0) return launch_contract_one<kBmEU>(s, which, beta, st) > 0 ? 0 : 2;
   if (beta != 1.0) return launch_contract_two(s, which, beta, st);
-  return launch_contract_any<false>(s, which, st) > 0 ? 0 : 2;
+  return launch_contract_one<kBmKL>(s, which, beta, st) > 0 ? 0 : 2;
 }
 
 }  // namespace
@@ -1331,7 +1478,7 @@ int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma,
   if (rc) return rc;
   rc = launch_contract(s, 0, beta, st);
   if (rc) return rc;
-  return apply_and_finish(s, 0, W, true, &s->plan_w, beta, gamma, l1, l2, st);
+  return apply_and_finish(s, 0, W, true, &s->plan_w, beta, gamma, l1, l2, st, nullptr, H);
 }
 
 int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma, double l1, double l2,
@@ -1340,7 +1487,7 @@ int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma,
   if (rc) return rc;
   rc = launch_contract(s, 1, beta, st);
   if (rc) return rc;
-  return apply_and_finish(s, 1, H, true, &s->plan_h, beta, gamma, l1, l2, st);
+  return apply_and_finish(s, 1, H, true, &s->plan_h, beta, gamma, l1, l2, st, nullptr, W);
 }
 
 int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double l1, double l2, int n_iter,
@@ -1480,14 +1627,15 @@ int tc_loss(TcState* s, const float* W, const float* H, double beta, double* los
     NMF_LAUNCH_CHECK();
     return 0;
   }
-  if (s->vbeta_for != beta) {      // V-only term of this beta, once per (target, beta)
+  if (beta != 2.0 && s->vbeta_for != beta) {      // V-only term of this beta, once per (target, beta)
     v_beta_term_kernel<<<1024, 256, 0, st>>>(s->Vsrc, s->N, s->C, s->ldv, (float)beta, s->vbeta_part);
     NMF_LAUNCH_CHECK();
     sum_blocks_kernel<<<1, 256, 0, st>>>(s->vbeta_part, 1024, s->vbeta);
     NMF_LAUNCH_CHECK();
     s->vbeta_for = beta;
   }
-  int grid = beta == 0.0 ? launch_loss_bm<kBmIS>(s, beta, st) : launch_loss_bm<kBmGen>(s, beta, st);
+  int grid = beta == 2.0 ? launch_loss_bm<kBmEU>(s, beta, st)
+                         : (beta == 0.0 ? launch_loss_bm<kBmIS>(s, beta, st) : launch_loss_bm<kBmGen>(s, beta, st));
   if (grid <= 0) return 2;
   tc_loss_final_beta_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vbeta, beta, (double)s->N * (double)s->C, loss_dev);
   NMF_LAUNCH_CHECK();

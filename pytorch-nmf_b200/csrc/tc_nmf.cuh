@@ -12,6 +12,8 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
 void tc_destroy(TcState* s);
 bool tc_supports_beta(const TcState* s, double beta);
 bool tc_supports_loss(const TcState* s, double beta);
+// row-sharded partials: beta 2 keeps the fp32 contraction (its numerator needs the Gram matrix of the global H)
+bool tc_supports_partial(const TcState* s, double beta);
 // minmax_dev: device float[2] = {min(V), max(V)} already queued on `st`
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st);
 // the fp32 factor changed outside the tensor-core path: operand copies must be rebuilt before use

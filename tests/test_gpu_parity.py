@@ -314,3 +314,39 @@ def test_tc_loss_other_betas_match_oracle(beta, precision):
     got = eng.loss(beta)
     eng.close()
     assert math.isclose(got, want, rel_tol=3e-4), (beta, got, want)
+
+
+# ---- beta == 2 on tensor cores: residual tile (V - WH), numerator = O + W (H^T H) -------------------------------
+@pytest.mark.parametrize("shape", [(384, 256, 64), (1000, 700, 20), (130, 2049, 33), (512, 384, 128)])
+@pytest.mark.parametrize("precision", ["f16", "f16_split"])
+def test_tc_frobenius_updates_match_oracle(shape, precision):
+    N, C, R = shape
+    torch.manual_seed(N + C + R)
+    V = torch.rand(N, C)
+    W0 = torch.rand(C, R) + 0.05
+    H0 = torch.rand(N, R) * 3 + 0.01
+    from torchnmf_b200.engine import CudaNmfEngine
+    Wd, Hd = W0.cuda(), H0.cuda()
+    eng = CudaNmfEngine(V.cuda(), Wd, Hd, precision)
+    assert eng.precision_for(2) == precision
+    eng.update_w(2, 1.0, 0.0, 0.0)
+    Wn = orc.nmf_update_w(V, W0, H0, 2)
+    eng.update_h(2, 1.0, 0.01, 0.02)
+    Hn = orc.nmf_update_h(V, Wn, H0, 2, 1.0, 0.01, 0.02)
+    want = float(orc.beta_div(orc.nmf_reconstruct(Hn, Wn).double(), V.double(), 2))
+    got = eng.loss(2)
+    eng.close()
+    tol = 1e-3 if precision == "f16_split" else 3e-3      # single-rounded fp16 factors enter S directly here
+    assert _close(Wd.cpu(), Wn, tol, 1e-5)[0], _close(Wd.cpu(), Wn, tol, 1e-5)[1]
+    assert _close(Hd.cpu(), Hn, tol, 1e-5)[0], _close(Hd.cpu(), Hn, tol, 1e-5)[1]
+    assert math.isclose(got, want, rel_tol=5e-3), (got, want)
+
+
+@pytest.mark.parametrize("name", ["nmf_cfg1", "nmf_b2_a0_l0", "nmf_b2_a0.1_l0.5"])
+def test_tc_frobenius_fit_matches_reference_golden(name):
+    c = CASES[name]                                     # nmf_cfg1 = BASELINE.json configs[0]: 256x512 R=16 beta=2, 50 iterations
+    m, n_iter = _run_case(c, "f16_split")
+    assert m.last_fit_precision == "f16_split" and n_iter == c["n_iter"]
+    for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
+        ok, err = _close(got, want, TC_RTOL, TC_ATOL_REL)
+        assert ok, f"{name} {nm}: scaled err {err:.3e}"
