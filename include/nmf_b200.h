@@ -37,7 +37,7 @@ extern "C" {
 
 /* arithmetic mode of the contraction kernels */
 enum {
-  NMFB200_PREC_AUTO      = -1, /* f16 split tensor-core path when shape/beta allow it, else f32   */
+  NMFB200_PREC_AUTO      = -1, /* f16 tensor-core path when the rank allows it (R <= 128), else f32 */
   NMFB200_PREC_F32       = 0,  /* fused CUDA-core kernels, fp32 operands and accumulators (exact) */
   NMFB200_PREC_F16       = 1,  /* tcgen05, fp16 operands, fp32 accumulate                         */
   NMFB200_PREC_F16_SPLIT = 2   /* tcgen05, fp16 hi/lo split factors (~22-bit), fp16 ratio tile    */
