@@ -43,12 +43,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // in g_wait_abort and every wait in the grid then falls through, so the kernel terminates instead of hanging
 // the GPU box; the host checks the record after the launch (tc_nmf.cu: check_wait_abort).
 __device__ unsigned int g_wait_abort[8];
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+// Slow path of mbar_wait, out of line on purpose: the warp-specialised loops are latency-bound serial instruction
+// streams (one MMA-issuing warp feeds the whole SM), so every wait site inlines only try_wait + a predicated call.
+// The poll loop touches nothing but the barrier; the watchdog (clock, abort flag in global memory) is looked at once
+// per 1024 failed polls -- a global load per poll costs an L2 round trip under a saturated memory system and shows up
+// as microseconds of wake-up latency at every hand-off.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 1023u) != 0u) continue;
     if (*reinterpret_cast<volatile unsigned int*>(&g_wait_abort[0]) != 0u) return;
-    if (clock64() - t0 > 2000000000LL) {
+    const long long now = clock64();
+    if (t0 == 0) { t0 = now; continue; }
+    if (now - t0 > 2000000000LL) {
       if (atomicCAS(&g_wait_abort[0], 0u, 1u) == 0u) {
         g_wait_abort[1] = blockIdx.x; g_wait_abort[2] = threadIdx.x; g_wait_abort[3] = bar; g_wait_abort[4] = parity;
         __threadfence();
@@ -56,6 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       return;
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
@@ -123,6 +134,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {

@@ -6,7 +6,8 @@
 //   TMA      G tile [128 c][KW] and V tile [128 m][128 c] (fp16, SWIZZLE_128B) -> shared memory
 //   MMA-1    S[128 m][128 c]  = F_blk G_tile^T            tcgen05.mma SS, fp32 accumulators in TMEM
 //   ratio    P = V * rcp(S*c1 + c2)  (== V / (F G^T + eps), nmf.py:65); the CENTRED tile P - kappa -> fp16, written
-//            back to TMEM over the S columns it was computed from (128 threads per tile, one TMEM lane each)
+//            back to TMEM over S columns the writer has already read (256 threads per tile: two warpgroups, each all 128
+//            TMEM lanes x half the columns)
 //   MMA-2    O[128 m][KW]   += (P - kappa) G_tile          tcgen05.mma TS (A from TMEM, B = G tile MN-major)
 //            (numerator = O + kappa colsum(G), added in fp32 by the ratio stage)
 //
@@ -14,9 +15,10 @@
 // F/G are fp16 copies of the factors scaled by a power of two; in split mode they carry hi|lo halves
 // (KW = 2*Rp) and S = Fhi Ghi + Flo Ghi + Fhi Glo, O = P [Ghi|Glo] recovers ~22-bit factors.
 //
-// Warp roles (512 threads): 0 TMA producer for V (the HBM stream, own ring) | 1 MMA issuer (one lane) |
-// 2 TMA producer for F/G (L2-resident factors) | 4-7 ratio warpgroup A (even tiles) | 8-11 ratio warpgroup B
-// (odd tiles) | 12-15 epilogue (O -> fp32 partial numerators).  S runs two tiles ahead of O in the tensor pipe.
+// Warp roles (512 threads): 0 TMA producer for V (the HBM stream, own ring) | 1 MMA issuer for S (one lane) |
+// 2 TMA producer for F/G (L2-resident factors) | 3 MMA issuer for O | 4-7, 8-11 ratio warpgroups (left / right half of
+// the tile's columns) | 12-15 epilogue (O -> fp32 partial numerators).  S runs up to NS tiles ahead of O in the tensor
+// pipe, across work-item boundaries.
 #include "tc_nmf.cuh"
 
 #include <cuda.h>
@@ -38,11 +40,12 @@ constexpr uint32_t kColS = 0;        // S/P stages: columns [TN i, TN i + TN); O
 // Compile-time configuration of the fused kernel.
 //   RP    padded rank (64 or 128);  SPLIT  hi|lo fp16 factors (KW = 2 RP operand columns)
 //   TN    tile width in columns of V (64 or 128): narrower tiles = deeper rings in the same shared memory
-//   NF / NG / NV  F blocks, G-tile ring, V-tile ring;  NS  S/P accumulator stages in TMEM;  AHEAD  S lookahead
-//   NRW   ratio warpgroups (tile t is processed by warpgroup t % NRW)
-template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int AHEAD_, int NRW_ = 2>
+//   NF / NG / NV  F blocks, G-tile ring, V-tile ring;  NS  S/P accumulator stages in TMEM (the S-MMA warp runs up to
+//   NS tiles ahead of the O-MMA warp)
+//   NRW   ratio warpgroups (each processes TN / NRW columns of every tile)
+template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int NRW_ = 2>
 struct Cfg {
-  static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, AHEAD = AHEAD_, NRW = NRW_;
+  static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, NRW = NRW_;
   // warps 0-3: TMA (V) / MMA / TMA (F,G) / spare; then 4 NRW ratio warps; then 4 epilogue warps
   static constexpr int kThreads = 128 + 128 * NRW_ + 128;
   static constexpr bool SPLIT = SPLIT_;
@@ -63,14 +66,22 @@ struct TcKernelParams {
   double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
   const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
   int pf_dist;                // L2 prefetch distance of the V stream in tiles (0 = off)
-  int skip_g;                 // tuning experiment: skip the G-tile loads after the first ring fill (results invalid)
   long long* trace;           // tuning aid: per-tile event timestamps of CTA 0 ([tile][12]), or nullptr
+  int knock;                  // tuning build only (NMFB200_TC_KNOCK): bit mask of pipeline stages to skip
 };
 
+// Event timeline of CTA 0 (tools/tc_trace.py): compiled in only with -DNMFB200_TRACE (build.py: NMFB200_BUILD_TRACE=1);
+// the product build carries no trace code in the warp-specialised loops.
+#ifdef NMFB200_TRACE
 #define TC_TRACE(tile, k)                                                        \
   do {                                                                         \
     if (p.trace && blockIdx.x == 0 && (tile) < 256) p.trace[(tile) * 12 + (k)] = clock64(); \
   } while (0)
+#define TC_KNOCK(bit) ((p.knock & (bit)) != 0)      // knock-out experiments (results invalid): which stage bounds the kernel?
+#else
+#define TC_TRACE(tile, k) do { } while (0)
+#define TC_KNOCK(bit) false
+#endif
 
 // shared memory: NF F blocks | NG G-tile ring | NV V-tile ring | mbarriers | tmem ptr | loss slots
 template <int KW, int TN, int NF, int NG, int NV, int NS>
@@ -82,7 +93,7 @@ struct SmemLayout {
   static constexpr int kG = kF + NF * kFBytes;
   static constexpr int kV = kG + NG * kGBytes;
   static constexpr int kBar = kV + NV * kVBytes;
-  static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 2 * NS + 2;
+  static constexpr int kNumBars = 2 * NF + 2 * NG + 2 * NV + 3 * NS + 2;
   static constexpr int kTmemPtr = kBar + 8 * kNumBars;
   static constexpr int kLossSlots = kTmemPtr + 16;
   static constexpr int kTotal = kLossSlots + 16 * 16;
@@ -100,7 +111,7 @@ template <class C, int BM, bool LOSS>
 __global__ void __launch_bounds__(C::kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
-  constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS, AHEAD = C::AHEAD;
+  constexpr int RP = C::RP, KW = C::KW, TN = C::TN, NF = C::NF, NG = C::NG, NV = C::NV, NS = C::NS;
   constexpr bool SPLIT = C::SPLIT;
   constexpr int NRW = C::NRW;
   constexpr int kEpiWarp0 = 4 + 4 * NRW;          // first epilogue warp
@@ -125,7 +136,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_FFULL = 0, B_FEMPTY = NF, B_GFULL = 2 * NF, B_GEMPTY = B_GFULL + NG, B_VFULL = B_GEMPTY + NG,
                 B_VEMPTY = B_VFULL + NV, B_SFULL = B_VEMPTY + NV, B_PFULL = B_SFULL + NS,
-                B_OFULL = B_PFULL + NS, B_OEMPTY = B_OFULL + 1;
+                B_PEMPTY = B_PFULL + NS, B_OFULL = B_PEMPTY + NS, B_OEMPTY = B_OFULL + 1;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + L::kTmemPtr);
   double* loss_slots = reinterpret_cast<double*>(smem_al + L::kLossSlots);      // [8 ratio warps][2]
 
@@ -135,8 +146,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     ptx::prefetch_tmap(&tmF); ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(&tmV);
     for (int i = 0; i < NF; ++i) { ptx::mbar_init(BAR(B_FFULL + i), 1); ptx::mbar_init(BAR(B_FEMPTY + i), 1); }
     for (int i = 0; i < NG; ++i) { ptx::mbar_init(BAR(B_GFULL + i), 1); ptx::mbar_init(BAR(B_GEMPTY + i), 1); }
-    for (int i = 0; i < NV; ++i) { ptx::mbar_init(BAR(B_VFULL + i), 1); ptx::mbar_init(BAR(B_VEMPTY + i), 128); }
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128); }
+    for (int i = 0; i < NV; ++i) { ptx::mbar_init(BAR(B_VFULL + i), 1); ptx::mbar_init(BAR(B_VEMPTY + i), 128 * NRW); }
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(BAR(B_SFULL + i), 1); ptx::mbar_init(BAR(B_PFULL + i), 128 * NRW); ptx::mbar_init(BAR(B_PEMPTY + i), 1);
+    }
     ptx::mbar_init(BAR(B_OFULL), 1);
     ptx::mbar_init(BAR(B_OEMPTY), 128);
     ptx::fence_barrier_init();
@@ -189,6 +202,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           if (kPfDist > 0) pf_issue_and_advance();
           ptx::mbar_wait(BAR(B_VEMPTY + s), ph ^ 1);
           TC_TRACE(t, 7);
+          if (TC_KNOCK(32) && t >= (uint32_t)NV) { ptx::mbar_arrive(BAR(B_VFULL + s)); continue; }
           ptx::mbar_expect_tx(BAR(B_VFULL + s), L::kVBytes);
           for (int vb = 0; vb < TN / 64; ++vb)
             ptx::tma_load_2d(&tmV, BAR(B_VFULL + s), sV + s * L::kVBytes + vb * (kTileM * 128), j * TN + vb * 64,
@@ -213,7 +227,6 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           const uint32_t s = t % NG, ph = (t / NG) & 1;
           ptx::mbar_wait(BAR(B_GEMPTY + s), ph ^ 1);
           TC_TRACE(t, 8);
-          if (p.skip_g && t >= (uint32_t)NG) { ptx::mbar_arrive(BAR(B_GFULL + s)); continue; }
           ptx::mbar_expect_tx(BAR(B_GFULL + s), L::kGBytes);
           for (int kb = 0; kb < KW / 64; ++kb)
             ptx::tma_load_2d(&tmG, BAR(B_GFULL + s), sG + s * L::kGBytes + kb * (TN * 128), kb * 64, j * TN);
@@ -221,39 +234,35 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer =============================
-    // The whole warp runs this loop with warp-uniform values (ring cursors, descriptors live in uniform
-    // registers); only the tcgen05.mma / commit instructions are issued by one elected lane.
+    // =========================== MMA issuer 1: S = F G^T =============================
+    // Two issuing warps share the tensor pipe.  An issuing warp is a latency-bound serial instruction stream (barrier
+    // polls, descriptor arithmetic in uniform registers, tcgen05.mma issue: measured ~780 cycles per S or O step), so
+    // one warp issuing both S and O produced one tile per ~1570 cycles and left the ratio warpgroups waiting for S.
+    // This warp runs ahead with the S-MMAs, across work-item boundaries, bounded by the G ring and by the NS
+    // accumulator stages (p_empty: the O-MMA of the tile NS earlier has consumed the stage); warp 3 issues the O-MMAs as
+    // ratio tiles complete.  Each loop is warp-uniform; one elected lane issues tcgen05.mma / commit.
     {
       constexpr uint32_t idescS = ptx::idesc_f16(kTileM, TN, 0, 0);
-      constexpr uint32_t idescO = ptx::idesc_f16(kTileM, KW, 0, 1);
       constexpr uint32_t descHi = ptx::smem_desc_hi_sw128(1024);
       // S = sum over terms (F part, G part): fast: (0,0); split: (hi,hi), (lo,hi), (hi,lo)
       constexpr int kTerms = SPLIT ? 3 : 1;
       constexpr int termF[3] = {0, 1, 0}, termG[3] = {0, 0, 1};
+      uint32_t sg = 0, sg_ph = 0;                 // G stage / phase
+      uint32_t ss = 0, ss_ph = 0;                 // S stage / phase of its p_empty barrier
+      uint32_t ts = 0;                            // tile counter (trace only)
       uint32_t it = 0;
-      uint32_t f_s = 0, f_ph = 0;                 // F block ring
-      uint32_t sg = 0, sg_ph = 0, ss = 0;         // next S issue: G stage/phase, S stage
-      uint32_t og = 0, os = 0, os_ph = 0;         // next O issue: G stage, S/P stage + p_full phase
-      uint32_t ts = 0, to = 0;                    // tile counters (trace only)
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        const int chunk = item / p.row_blocks;
-        const int tb = chunk * p.tiles_per_chunk;
-        const int te = min(p.tiles, tb + p.tiles_per_chunk);
-        const int n = te - tb;
-        if (lane == 0) ptx::mbar_wait(BAR(B_FFULL + f_s), f_ph);
+        const int tb = (item / p.row_blocks) * p.tiles_per_chunk;
+        const int n = min(p.tiles, tb + p.tiles_per_chunk) - tb;
+        const uint32_t f_s = it % NF;
+        if (lane == 0) ptx::mbar_wait(BAR(B_FFULL + f_s), (it / NF) & 1);       // F block of this item landed
         __syncwarp();      // one poller; the warp is converged again before any elect.sync / tcgen05 issue
-        ptx::tc_fence_after();
         const uint32_t fbase = sF + f_s * L::kFBytes;
-        const uint32_t f_bar = BAR(B_FEMPTY + f_s);
-        if (++f_s == NF) { f_s = 0; f_ph ^= 1; }
-
-        // S stage of a tile is free once the O-MMA of the tile NS earlier consumed its P: that MMA was
-        // issued earlier by this warp, and the tensor pipe executes in issue order.
-        auto issue_S = [&]() {
+        for (int j = 0; j < n; ++j) {
           if (lane == 0) {
             TC_TRACE(ts, 0);
-            ptx::mbar_wait(BAR(B_GFULL + sg), sg_ph);
+            ptx::mbar_wait(BAR(B_GFULL + sg), sg_ph);              // G tile landed
+            ptx::mbar_wait(BAR(B_PEMPTY + ss), ss_ph ^ 1);         // O-MMA of the tile NS earlier consumed this stage
             TC_TRACE(ts, 1);
           }
           __syncwarp();
@@ -263,6 +272,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           if (ptx::elect_one()) {
 #pragma unroll
             for (int term = 0; term < kTerms; ++term) {
+              if (TC_KNOCK(16)) break;
               // operand halves (hi / lo) are RP/64 sub-blocks of 64 columns each; a k-step is 32 B inside a sub-block
 #pragma unroll
               for (int ks = 0; ks < RP / 16; ++ks) {
@@ -273,23 +283,41 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
               }
             }
             ptx::mma_commit(BAR(B_SFULL + ss));
+            if (j == n - 1) ptx::mma_commit(BAR(B_FEMPTY + f_s));  // last S of the item: its F block is free
           }
           __syncwarp();
           if (++sg == NG) { sg = 0; sg_ph ^= 1; }
-          if (++ss == NS) ss = 0;
+          if (++ss == NS) { ss = 0; ss_ph ^= 1; }
           ++ts;
-        };
-        auto issue_O = [&](bool first, bool last) {
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== MMA issuer 2: O += P G =============================
+    {
+      constexpr uint32_t idescO = ptx::idesc_f16(kTileM, KW, 0, 1);
+      constexpr uint32_t descHi = ptx::smem_desc_hi_sw128(1024);
+      uint32_t og = 0, os = 0, os_ph = 0;         // G stage, S/P stage + p_full phase
+      uint32_t to = 0;                            // tile counter (trace only)
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int tb = (item / p.row_blocks) * p.tiles_per_chunk;
+        const int n = min(p.tiles, tb + p.tiles_per_chunk) - tb;
+        for (int j = 0; j < n; ++j) {
+          const bool first = j == 0, last = j == n - 1;
           if (lane == 0) {
             TC_TRACE(to, 5);
-            ptx::mbar_wait(BAR(B_PFULL + os), os_ph);
-            if (first && !LOSS) ptx::mbar_wait(BAR(B_OEMPTY), (it & 1) ^ 1);   // (no epilogue in LOSS mode)
+            ptx::mbar_wait(BAR(B_PFULL + os), os_ph);                              // ratio tile written
+            if (first && !LOSS) ptx::mbar_wait(BAR(B_OEMPTY), (it & 1) ^ 1);       // epilogue drained O (none in LOSS mode)
             TC_TRACE(to, 6);
           }
           __syncwarp();
           ptx::tc_fence_after();
           if (LOSS) {
-            if (ptx::elect_one()) ptx::mbar_arrive(BAR(B_GEMPTY + og));    // ratio warpgroup consumed S
+            if (ptx::elect_one()) {                    // nothing to multiply: the ratio warpgroup consumed S, release
+              ptx::mbar_arrive(BAR(B_GEMPTY + og));
+              ptx::mbar_arrive(BAR(B_PEMPTY + os));
+            }
           } else {
             // B = G tile as [K = 16 c-rows][N = KW] MN-major: 8-row groups 1024 B apart, 64-wide column blocks
             // (hi | lo, RP/64 blocks each) one sub-block (TN x 128 B) apart
@@ -298,13 +326,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < TN / 16; ++ks) {
-                ptx::mma_ts(tmem + kColO, aP + ks * 8, ptx::make_desc(blo + ks * 128, descHi), idescO,
-                            (first && ks == 0) ? 0u : 1u);
+                if (TC_KNOCK(8)) break;
+                // P k-step ks was written by ratio warpgroup ks / kKsPerWg at the start of that warpgroup's columns
+                constexpr int kKsPerWg = TN / 16 / NRW;
+                ptx::mma_ts(tmem + kColO, aP + (ks / kKsPerWg) * (TN / NRW) + (ks % kKsPerWg) * 8,
+                            ptx::make_desc(blo + ks * 128, descHi), idescO, (first && ks == 0) ? 0u : 1u);
                 if (TWO)
                   ptx::mma_ts(tmem + kColO2, tmem + kColPp + os * 64 + ks * 8, ptx::make_desc(blo + ks * 128, descHi),
                               idescO, (first && ks == 0) ? 0u : 1u);
               }
-              ptx::mma_commit(BAR(B_GEMPTY + og));
+              ptx::mma_commit(BAR(B_GEMPTY + og));     // G tile free (its S-MMA finished before the ratio tile existed)
+              ptx::mma_commit(BAR(B_PEMPTY + os));     // S/P stage free
               if (last) ptx::mma_commit(BAR(B_OFULL));
             }
           }
@@ -312,26 +344,16 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           if (++og == NG) og = 0;
           if (++os == NS) { os = 0; os_ph ^= 1; }
           ++to;
-        };
-
-        // software pipeline: S runs AHEAD tiles ahead of O (needs AHEAD < NS and NG >= AHEAD + 2 to hide
-        // the G-tile reload behind the tensor pipe)
-        constexpr int kAhead = AHEAD;
-        static_assert(AHEAD >= 1 && AHEAD < NS, "S lookahead");
-        for (int j = 0; j < kAhead && j < n; ++j) issue_S();
-        if (n <= kAhead && ptx::elect_one()) ptx::mma_commit(f_bar);
-        for (int j = 0; j < n; ++j) {
-          if (j + kAhead < n) {
-            issue_S();
-            if (j + kAhead == n - 1 && ptx::elect_one()) ptx::mma_commit(f_bar);   // last S of the item issued
-          }
-          issue_O(j == 0, j == n - 1);
         }
       }
     }
   } else if (warp >= 4 && warp < kEpiWarp0) {
     // =========================== ratio warpgroups =======================
-    const int g = (warp - 4) >> 2;             // this warpgroup handles tiles t with t % NRW == g
+    // Every tile is split by COLUMNS between the NRW ratio warpgroups (each covers all 128 TMEM lanes): the time a tile
+    // spends in the ratio stage is what holds its S/P accumulator stage, and with NS = 3 stages that hold time -- not
+    // MUFU, shared-memory or HBM throughput -- set the tile period (knock-out timing).  Splitting a
+    // tile halves the hold; alternating whole tiles between the warpgroups did not.
+    const int g = (warp - 4) >> 2;             // this warpgroup handles columns [g TN / NRW, (g + 1) TN / NRW) of every tile
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -357,6 +379,81 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     double accA = 0.0, accB = 0.0;
     uint32_t t = 0;
     const float vinv = exp2f(-(float)ev);
+    if constexpr (!LOSS && !TWO) {
+      // ---- update tiles of beta 1 / beta 2: one flat loop over this CTA's tiles, software-pipelined over 16-column chunks:
+      // the TMEM load of S and the shared-memory load of V for chunk c + 1 are in flight while chunk c is computed.
+      // (Also tried, no gain on the B200: starting the next tile's first chunk before the last chunk of this tile is
+      // computed; FMA-pipe reciprocals for a quarter of the elements; parked try_wait.  DESIGN.md 4.1.)
+      constexpr int kChunks = TN / 16;
+      constexpr int kCpw = kChunks / NRW;                       // chunks per warpgroup and tile
+      static_assert(kCpw % 2 == 0 && kChunks % NRW == 0, "chunks per ratio warpgroup");
+      const int c_lo = g * kCpw;
+      uint32_t my_tiles = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tb = (item / p.row_blocks) * p.tiles_per_chunk;
+        my_tiles += min(p.tiles, tb + p.tiles_per_chunk) - tb;
+      }
+      uint32_t sA[16], sB[16];
+      uint4 vA[2], vB[2];
+      auto load_chunk = [&](uint32_t tile, int c, uint32_t (&sr)[16], uint4 (&vv)[2]) {
+        ptx::tmem_ld16(tmem + lane_addr + kColS + (tile % NS) * TN + c * 16, sr);
+        const uint32_t vsub = sV + (tile % NV) * L::kVBytes + row * 128 + (c >> 2) * (kTileM * 128);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (TC_KNOCK(2)) { vv[k] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u); continue; }
+          const uint32_t chunk16 = (uint32_t)((c & 3) * 2 + k) ^ (uint32_t)(row & 7);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(vv[k].x), "=r"(vv[k].y), "=r"(vv[k].z), "=r"(vv[k].w)
+                       : "r"(vsub + (chunk16 << 4)));
+        }
+      };
+      auto compute_chunk = [&](uint32_t tile, int c, const uint32_t (&sr)[16], const uint4 (&vv)[2]) {
+        const uint32_t* vw = reinterpret_cast<const uint32_t*>(vv);
+        uint32_t preg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
+          float p0, p1;
+          if (EU) {
+            p0 = fmaf(vf.x, eu_cv, -__uint_as_float(sr[2 * i]) * eu_cs);            // nmf.py:62-63: V - WH
+            p1 = fmaf(vf.y, eu_cv, -__uint_as_float(sr[2 * i + 1]) * eu_cs);
+          } else {
+            const float x0 = fmaf(__uint_as_float(sr[2 * i]), c1, c2);
+            const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), c1, c2);
+            p0 = fmaf(vf.x, TC_KNOCK(1) ? x0 : ptx::rcp_approx(x0), negpc);         // nmf.py:65, centred
+            p1 = fmaf(vf.y, TC_KNOCK(1) ? x1 : ptx::rcp_approx(x1), negpc);
+          }
+          preg[i] = TC_KNOCK(4) ? sr[i] : ptx::pack_f16x2_sat(p0, p1);
+        }
+        // P of warpgroup g goes over the S columns that warpgroup owns (and has already read): [g TN / NRW, ...)
+        ptx::tmem_st8(tmem + lane_addr + kColS + (tile % NS) * TN + g * (TN / NRW) + (c - c_lo) * 8, preg);
+      };
+      for (uint32_t tt = 0; tt < my_tiles; ++tt) {
+        const uint32_t s = tt % NV, st = tt % NS;
+        if (q == 0 && lane == 0) TC_TRACE(tt, 2);
+        ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);        // V tile landed (TMA -> this thread)
+        if (q == 0 && lane == 0) TC_TRACE(tt, 3);
+        ptx::mbar_wait(BAR(B_SFULL + st), (tt / NS) & 1);       // S tile complete
+        if (q == 0 && lane == 0) TC_TRACE(tt, 4);
+        ptx::tc_fence_after();
+        load_chunk(tt, c_lo, sA, vA);
+#pragma unroll
+        for (int cc = 0; cc < kCpw; cc += 2) {
+          const int c = c_lo + cc;
+          ptx::tc_wait_ld();
+          load_chunk(tt, c + 1, sB, vB);
+          compute_chunk(tt, c, sA, vA);
+          ptx::tc_wait_ld();
+          if (cc + 2 < kCpw) load_chunk(tt, c + 2, sA, vA);
+          compute_chunk(tt, c + 1, sB, vB);
+        }
+        ptx::tc_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(BAR(B_PFULL + st));
+        ptx::mbar_arrive(BAR(B_VEMPTY + s));
+        if (q == 0 && lane == 0) TC_TRACE(tt, 9);
+      }
+    } else {
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int chunk = item / p.row_blocks;
       const int tb = chunk * p.tiles_per_chunk;
@@ -365,7 +462,6 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       const bool row_ok = (item % p.row_blocks) * kTileM + row < p.Mr;
       for (int j = 0; j < n; ++j) {
         const uint32_t tt = t + j;
-        if ((int)(tt % NRW) != g) continue;
         const uint32_t s = tt % NV, st = tt % NS;
         if (q == 0 && lane == 0) TC_TRACE(tt, 2);
         ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);              // V tile landed (TMA -> this thread)
@@ -374,14 +470,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         if (q == 0 && lane == 0) TC_TRACE(tt, 4);
         ptx::tc_fence_after();
         const uint32_t vrow = sV + s * L::kVBytes + row * 128;
+        {
 #pragma unroll
-        for (int c4 = 0; c4 < TN / 32; ++c4) {
+        for (int c4r = 0; c4r < TN / 32 / NRW; ++c4r) {
+          const int c4 = g * (TN / 32 / NRW) + c4r;
           uint32_t sreg[32];
           ptx::tmem_ld32(tmem + lane_addr + kColS + st * TN + c4 * 32, sreg);
           uint4 vv[4];
           const uint32_t vsub = vrow + (c4 >> 1) * (kTileM * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (TC_KNOCK(2)) { vv[k] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u); continue; }
             const uint32_t chunk16 = (uint32_t)((c4 & 1) * 4 + k) ^ (uint32_t)(row & 7);
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(vv[k].x), "=r"(vv[k].y), "=r"(vv[k].z), "=r"(vv[k].w)
@@ -441,16 +540,6 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             }
             accA += (double)la;
             accB += (double)lb;
-          } else if (EU) {
-            uint32_t preg[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
-              const float p0 = fmaf(vf.x, eu_cv, -__uint_as_float(sreg[2 * i]) * eu_cs);      // nmf.py:62-63: V - WH
-              const float p1 = fmaf(vf.y, eu_cv, -__uint_as_float(sreg[2 * i + 1]) * eu_cs);
-              preg[i] = ptx::pack_f16x2_sat(p0, p1);
-            }
-            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, preg);
           } else if (TWO) {
             uint32_t pn[16], pp[16];
 #pragma unroll
@@ -477,21 +566,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
               pn[i] = ptx::pack_f16x2_sat(vf.x * fn[0] * kn, vf.y * fn[1] * kn);
               pp[i] = ptx::pack_f16x2_sat(fp[0] * kd, fp[1] * kd);
             }
-            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, pn);
+            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + g * (TN / NRW) + c4r * 16, pn);   // own S columns, see above
             ptx::tmem_st16(tmem + lane_addr + kColPp + st * 64 + c4 * 16, pp);
-          } else {
-            uint32_t preg[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
-              const float x0 = fmaf(__uint_as_float(sreg[2 * i]), c1, c2);
-              const float x1 = fmaf(__uint_as_float(sreg[2 * i + 1]), c1, c2);
-              const float p0 = fmaf(vf.x, ptx::rcp_approx(x0), negpc);
-              const float p1 = fmaf(vf.y, ptx::rcp_approx(x1), negpc);
-              preg[i] = ptx::pack_f16x2_sat(p0, p1);
-            }
-            ptx::tmem_st16(tmem + lane_addr + kColS + st * TN + c4 * 16, preg);
           }
+        }
         }
         if (!LOSS) ptx::tc_wait_st();
         ptx::tc_fence_before();
@@ -501,6 +579,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       }
       t += n;
     }
+    }   // LOSS and two-output kernels
     if (LOSS) {
       for (int o = 16; o > 0; o >>= 1) {
         accA += __shfl_xor_sync(0xffffffffu, accA, o);
@@ -1400,8 +1479,8 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   p.loss_part = s->loss_part;
   p.kappa = s->kappa;
   p.trace = s->trace;
+  p.knock = getenv("NMFB200_TC_KNOCK") ? atoi(getenv("NMFB200_TC_KNOCK")) : 0;
   p.pf_dist = s->pf_dist;
-  p.skip_g = getenv("NMFB200_TC_SKIPG") ? 1 : 0;
   if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 12 * sizeof(long long), st);
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
@@ -1413,26 +1492,32 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   return grid;
 }
 
-// Kernel configurations <RP, SPLIT, TN, NF, NG, NV, NS, AHEAD> (224 KB of shared memory each).  Tuning notes in
-// profiles/README.md: the V ring must keep >= 3 tiles (>= 64 KB) in flight to cover HBM latency, the G ring needs
-// >= AHEAD + 2 stages, and AHEAD = 2 lets both ratio warpgroups work concurrently.
-using CfgFast64 = Cfg<64, false, 128, 2, 4, 4, 3, 2>;      // F 2x16 | G 4x16 | V 4x32 KB ; TMEM 3x128 + 64
-using CfgSplit64 = Cfg<64, true, 128, 1, 3, 3, 3, 1>;       // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
-using CfgSplit64N = Cfg<64, true, 64, 1, 6, 6, 4, 2>;       // (variant 1) 64-column tiles, deeper rings: slower, MMA-issue bound
-using CfgFast128 = Cfg<128, false, 128, 1, 3, 3, 3, 1>;     // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
-using CfgSplit128 = Cfg<128, true, 64, 1, 3, 4, 4, 1>;      // F 64 | G 3x32 | V 4x16 KB     ; TMEM 4x64 + 256
+// Kernel configurations <RP, SPLIT, TN, NF, NG, NV, NS> (224 KB of shared memory each).  Tuning notes in
+// profiles/README.md and DESIGN.md 4.1: the V ring must keep >= 3 tiles (>= 64 KB) in flight to cover HBM latency, the G
+// ring needs >= 4 stages (a G tile stays resident from its S-MMA to its O-MMA); deeper G rings (5, 6) changed nothing.
+using CfgFast64 = Cfg<64, false, 128, 2, 4, 4, 3>;      // F 2x16 | G 4x16 | V 4x32 KB ; TMEM 3x128 + 64
+using CfgSplit64 = Cfg<64, true, 128, 1, 3, 3, 3>;       // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
+using CfgSplit64N = Cfg<64, true, 64, 1, 6, 6, 4>;       // (variant 1) 64-column tiles, deeper rings: slower
+using CfgFast128 = Cfg<128, false, 128, 1, 3, 3, 3>;     // F 32 | G 3x32 | V 3x32 KB     ; TMEM 3x128 + 128
+using CfgSplit128 = Cfg<128, true, 64, 1, 3, 4, 4>;      // F 64 | G 3x32 | V 4x16 KB     ; TMEM 4x64 + 256
 
-using CfgFast64R3 = Cfg<64, false, 128, 2, 4, 4, 3, 2, 3>;    // three ratio warpgroups (one per S stage), 640 threads
-using CfgSplit64R3 = Cfg<64, true, 128, 1, 3, 3, 3, 1, 3>;
-using CfgTwo64 = Cfg<64, false, 128, 2, 3, 4, 2, 1>;        // beta != 1: F 2x16 | G 3x16 | V 4x32 KB ; TMEM 2x128 + 128 + 2x64
+#ifdef NMFB200_TRACE    // tuning build: ring-depth experiments (NMFB200_TC_VARIANT = 4, 5, 6)
+using CfgFast64V4 = Cfg<64, false, 128, 1, 5, 4, 3>;
+using CfgFast64V5 = Cfg<64, false, 128, 1, 6, 3, 3>;
+using CfgFast64V6 = Cfg<64, false, 128, 1, 3, 5, 3>;
+#endif
+using CfgTwo64 = Cfg<64, false, 128, 2, 3, 4, 2>;        // beta != 1: F 2x16 | G 3x16 | V 4x32 KB ; TMEM 2x128 + 128 + 2x64
 
 // one-output kernels (beta 1: BM = kBmKL, beta 2: BM = kBmEU) over the configuration of this context
 template <int BM>
 int launch_contract_one(TcState* s, int which, double beta, cudaStream_t st) {
-  if (s->Rp == 64 && BM == kBmKL && s->variant == 3) {
-    if (!s->split) return launch_contract_t<CfgFast64R3, BM, false>(s, which, beta, st);
-    return launch_contract_t<CfgSplit64R3, BM, false>(s, which, beta, st);
+#ifdef NMFB200_TRACE
+  if (s->Rp == 64 && BM == kBmKL && !s->split) {
+    if (s->variant == 4) return launch_contract_t<CfgFast64V4, BM, false>(s, which, beta, st);
+    if (s->variant == 5) return launch_contract_t<CfgFast64V5, BM, false>(s, which, beta, st);
+    if (s->variant == 6) return launch_contract_t<CfgFast64V6, BM, false>(s, which, beta, st);
   }
+#endif
   if (s->Rp == 64) {
     if (!s->split) return launch_contract_t<CfgFast64, BM, false>(s, which, beta, st);
     if (s->TN == 64) return launch_contract_t<CfgSplit64N, BM, false>(s, which, beta, st);

@@ -1,6 +1,7 @@
 """Dump the per-tile event timeline of CTA 0 of the fused contraction kernel (tuning aid)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("NMFB200_LIB", os.path.join(ROOT, "pytorch-nmf_b200", "lib", "trace", "libnmf_b200.so"))   # tuning build
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-nmf_b200")]
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16"
 which = int(sys.argv[2]) if len(sys.argv) > 2 else 1
