@@ -25,6 +25,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "sm100_ptx.cuh"
@@ -1239,11 +1240,17 @@ struct TcState {
   cudaStream_t gstream = nullptr;   // capture / replay stream (the caller's may be the legacy default stream, which cannot capture)
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   bool dirty_w = true, dirty_h = true, has_target = false;
+  // Environment knobs, read once in tc_create.  Product build: NMFB200_CENTER=0 (diagnostic: kappa centring off, see
+  // tools/bias_probe.py), NMFB200_GRAPH=1 (CUDA-graph replay of tc_iterate), NMFB200_TC_CHECK=1 (watchdog check after
+  // every tc_contract_only).  Tuning build (-DNMFB200_TRACE) only: NMFB200_TC_VARIANT, NMFB200_TC_PF, NMFB200_TC_KNOCK,
+  // NMFB200_TC_TRACE=<file>.
   int center = 1;
-  int pf_dist = 0;
-  int variant = 0;                  // pipeline configuration (NMFB200_TC_VARIANT, tuning aid)
-  long long* trace = nullptr;       // NMFB200_TC_TRACE=<file>: event timestamps of CTA 0 (tuning aid)
-  const char* trace_path = nullptr;
+  bool use_graph = false, check_each = false;
+  int pf_dist = 0;                  // L2 prefetch distance of the V stream in tiles (measured: no gain; 0 = off)
+  int variant = 0;                  // pipeline configuration variant
+  int knock = 0;                    // knock-out mask (tools/tc_knock.py)
+  long long* trace = nullptr;       // event timestamps of CTA 0 (tools/tc_trace.py)
+  std::string trace_path;
   float* kappa = nullptr;           // device scalar
   float* zero = nullptr;            // device scalar 0 (kappa of an already complete numerator)
 };
@@ -1274,16 +1281,21 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   *out = nullptr;
   TcState* s = new TcState();
   s->device = device; s->N = N; s->C = C; s->R = R; s->split = split;
-  if (const char* e = getenv("NMFB200_TC_VARIANT")) s->variant = atoi(e);
   s->Rp = R <= 64 ? 64 : 128;
   s->KW = split ? 2 * s->Rp : s->Rp;
   s->TN = (split && s->Rp == 128) ? 64 : 128;   // 64-column tiles only where 128 do not fit (measured slower: MMA issue rate)
   if (const char* e = getenv("NMFB200_CENTER")) s->center = atoi(e);
+  s->use_graph = getenv("NMFB200_GRAPH") != nullptr;
+  s->check_each = getenv("NMFB200_TC_CHECK") != nullptr;
+#ifdef NMFB200_TRACE
+  if (const char* e = getenv("NMFB200_TC_VARIANT")) s->variant = atoi(e);
   if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
+  if (const char* e = getenv("NMFB200_TC_KNOCK")) s->knock = atoi(e);
   if (const char* e = getenv("NMFB200_TC_TRACE")) {
     s->trace_path = e;
     if (cudaMalloc(&s->trace, 256 * 12 * sizeof(long long)) != cudaSuccess) s->trace = nullptr;
   }
+#endif
   s->ldc = round_up(C, 8);
   s->ldn = round_up(N, 8);
   cudaDeviceProp prop;
@@ -1479,7 +1491,7 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   p.loss_part = s->loss_part;
   p.kappa = s->kappa;
   p.trace = s->trace;
-  p.knock = getenv("NMFB200_TC_KNOCK") ? atoi(getenv("NMFB200_TC_KNOCK")) : 0;
+  p.knock = s->knock;
   p.pf_dist = s->pf_dist;
   if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 12 * sizeof(long long), st);
   const int items = pl.row_blocks * pl.nchunks;
@@ -1584,7 +1596,7 @@ int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double
   }
   // CUDA-graph replay of the iteration is opt-in (NMFB200_GRAPH=1): measured no gain at cfg2 -- the stream is never
   // launch-bound (profiles/README.md) -- so the default keeps plain stream-ordered launches.
-  const bool use_graph = getenv("NMFB200_GRAPH") != nullptr && s->trace == nullptr;
+  const bool use_graph = s->use_graph && s->trace == nullptr;
   cudaStream_t user = st;
   if (use_graph) {
     // run on an engine-owned stream, fenced against the caller's stream with events
@@ -1683,14 +1695,14 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
   int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
   rc = launch_contract(s, which, beta, st);
-  if (rc == 0 && getenv("NMFB200_TC_CHECK")) {
+  if (rc == 0 && s->check_each) {
     if (tc_check_wait_abort(st) > 0) { set_error("mbarrier wait aborted (protocol bug)"); return 2; }
   }
   if (rc == 0 && s->trace) {
     std::vector<long long> h(256 * 12);
     cudaMemcpyAsync(h.data(), s->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
-    if (FILE* f = fopen(s->trace_path, "w")) {
+    if (FILE* f = fopen(s->trace_path.c_str(), "w")) {
       for (int t = 0; t < 256; ++t) {
         for (int k = 0; k < 12; ++k) fprintf(f, "%lld ", h[t * 12 + k]);
         fprintf(f, "\n");

@@ -9,15 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ.setdefault("NMFB200_LIB", os.path.join(ROOT, "pytorch-nmf_b200", "lib", "trace", "libnmf_b200.so"))   # tuning build
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pytorch-nmf_b200")]
 import torch
-from torchnmf_b200.engine import CudaNmfEngine
+from torchnmf_b200.engine import CudaNmfEngine, release_workspaces
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16"
 N, C, R = 65536, 4096, 64
 torch.manual_seed(0)
 V = torch.rand(N, C, device="cuda").bfloat16().float()
 W = torch.randn(C, R, device="cuda").abs(); H = torch.randn(N, R, device="cuda").abs()
-eng = CudaNmfEngine(V, W, H, prec)
 for k in [0, 1, 2, 3, 4, 8, 16, 24, 32, 33, 35, 36, 40, 56, 60, 63]:
-    os.environ["NMFB200_TC_KNOCK"] = str(k)
+    os.environ["NMFB200_TC_KNOCK"] = str(k)       # read once per engine context
+    eng = CudaNmfEngine(V, W, H, prec)
     out = []
     for which in (0, 1):
         for _ in range(3): eng.contract_only(which, 1.0)
@@ -28,3 +28,4 @@ for k in [0, 1, 2, 3, 4, 8, 16, 24, 32, 33, 35, 36, 40, 56, 60, 63]:
         e1.record(); torch.cuda.synchronize()
         out.append(e0.elapsed_time(e1) / 10 * 1e3)
     print(f"knock {k:2d}: W {out[0]:7.1f} us  H {out[1]:7.1f} us", flush=True)
+    eng.close(); release_workspaces()
