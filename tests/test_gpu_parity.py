@@ -268,6 +268,31 @@ def test_tc_loss_matches_oracle(precision):
     assert math.isclose(got, want, rel_tol=5e-5), (got, want)
 
 
+def test_cfg2_full_size_kl_invariants_on_tensor_cores():
+    """Size-independent properties at BASELINE.json's full cfg2 shape (65536 x 4096, rank 64), default precision:
+    after a KL W update colsum(H W^T) == colsum(V), after the H update rowsum(H W^T) == rowsum(V) (exact up to eps for
+    beta = 1 without regularisation), and the divergence never increases (nmf.py:366-391, metrics.py:22)."""
+    torch.manual_seed(11)
+    N, C, R = 65536, 4096, 64
+    V = torch.rand(N, C, device="cuda").bfloat16().float()
+    m = NMF((N, C), R).cuda()
+    from torchnmf_b200.engine import CudaNmfEngine
+    eng = CudaNmfEngine(V, m.W.data, m.H.data, "auto")
+    assert eng.precision_for(1) == "f16"
+    vcol, vrow = V.sum(0), V.sum(1)
+    prev = eng.loss(1)
+    for it in range(3):
+        eng.update_w(1, 1.0, 0.0, 0.0)
+        assert torch.allclose(m.W.data @ m.H.data.sum(0), vcol, rtol=2e-3), it
+        eng.update_h(1, 1.0, 0.0, 0.0)
+        assert torch.allclose(m.H.data @ m.W.data.sum(0), vrow, rtol=2e-3), it
+        cur = eng.loss(1)
+        assert cur <= prev * (1 + 1e-4), (it, cur, prev)
+        prev = cur
+    eng.check_health()
+    eng.close()
+
+
 # ---- beta != 1 on tensor cores (two-output kernels: numerator and denominator accumulators) -------------------
 @pytest.mark.parametrize("beta", [-1, 0, 0.5, 1.5, 3])
 @pytest.mark.parametrize("shape", [(384, 256, 64), (1000, 700, 20), (130, 2049, 33)])
