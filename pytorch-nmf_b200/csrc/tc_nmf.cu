@@ -452,7 +452,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(B_PFULL + st));
         ptx::mbar_arrive(BAR(B_VEMPTY + s));
-        if (q == 0 && lane == 0) TC_TRACE(tt, 9);
+        // per-warp end times (tuning build): slot 9 = warpgroup 0 / quarter 0, 10 = warpgroup 0 / quarter 3,
+        // 11 = last warpgroup / quarter 3 -- the skew between them is the wait of the O-MMA on the 256 p_full arrivals
+        if (lane == 0 && g == 0 && q == 0) TC_TRACE(tt, 9);
+        if (lane == 0 && g == 0 && q == 3) TC_TRACE(tt, 10);
+        if (lane == 0 && g == NRW - 1 && q == 3) TC_TRACE(tt, 11);
       }
     } else {
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
