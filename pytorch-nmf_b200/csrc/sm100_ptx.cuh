@@ -198,6 +198,18 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- small math helpers ----------------------------------------------------------------------------
+// Reciprocal on the FMA pipe (x > 0, normal): integer seed (<= 12 % off) + three Newton steps -> < 1e-7 relative.
+// Staged for round 2 (tuning build, knock bit 64): moves a quarter of the ratio stage's reciprocals off the XU pipe,
+// which needs 1024 of the ~1250 cycles a tile spends in the ratio stage.
+__device__ __forceinline__ float rcp_fma(float x) {
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+  float e = fmaf(-x, r, 1.f);
+  r = fmaf(r, e, r);
+  e = fmaf(-x, r, 1.f);
+  r = fmaf(r, e, r);
+  e = fmaf(-x, r, 1.f);
+  return fmaf(r, e, r);
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -421,23 +421,31 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           } else {
             const float x0 = fmaf(__uint_as_float(sr[2 * i]), c1, c2);
             const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), c1, c2);
-            p0 = fmaf(vf.x, TC_KNOCK(1) ? x0 : ptx::rcp_approx(x0), negpc);         // nmf.py:65, centred
-            p1 = fmaf(vf.y, TC_KNOCK(1) ? x1 : ptx::rcp_approx(x1), negpc);
+            // (tuning build, bit 64: every fourth pair takes its reciprocals on the FMA pipe -- valid results)
+            const bool on_fma = TC_KNOCK(64) && (i & 3) == 3;
+            const float r0 = on_fma ? ptx::rcp_fma(x0) : ptx::rcp_approx(x0);
+            const float r1 = on_fma ? ptx::rcp_fma(x1) : ptx::rcp_approx(x1);
+            p0 = fmaf(vf.x, TC_KNOCK(1) ? x0 : r0, negpc);                          // nmf.py:65, centred
+            p1 = fmaf(vf.y, TC_KNOCK(1) ? x1 : r1, negpc);
           }
           preg[i] = TC_KNOCK(4) ? sr[i] : ptx::pack_f16x2_sat(p0, p1);
         }
         // P of warpgroup g goes over the S columns that warpgroup owns (and has already read): [g TN / NRW, ...)
         ptx::tmem_st8(tmem + lane_addr + kColS + (tile % NS) * TN + g * (TN / NRW) + (c - c_lo) * 8, preg);
       };
+      bool started = false;      // tuning build, bit 128: the first chunk of this tile was requested during the previous one
       for (uint32_t tt = 0; tt < my_tiles; ++tt) {
         const uint32_t s = tt % NV, st = tt % NS;
-        if (q == 0 && lane == 0) TC_TRACE(tt, 2);
-        ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);        // V tile landed (TMA -> this thread)
-        if (q == 0 && lane == 0) TC_TRACE(tt, 3);
-        ptx::mbar_wait(BAR(B_SFULL + st), (tt / NS) & 1);       // S tile complete
-        if (q == 0 && lane == 0) TC_TRACE(tt, 4);
-        ptx::tc_fence_after();
-        load_chunk(tt, c_lo, sA, vA);
+        if (!started) {
+          if (q == 0 && lane == 0) TC_TRACE(tt, 2);
+          ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);        // V tile landed (TMA -> this thread)
+          if (q == 0 && lane == 0) TC_TRACE(tt, 3);
+          ptx::mbar_wait(BAR(B_SFULL + st), (tt / NS) & 1);       // S tile complete
+          if (q == 0 && lane == 0) TC_TRACE(tt, 4);
+          ptx::tc_fence_after();
+          load_chunk(tt, c_lo, sA, vA);
+        }
+        started = false;
 #pragma unroll
         for (int cc = 0; cc < kCpw; cc += 2) {
           const int c = c_lo + cc;
@@ -445,7 +453,20 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           load_chunk(tt, c + 1, sB, vB);
           compute_chunk(tt, c, sA, vA);
           ptx::tc_wait_ld();
-          if (cc + 2 < kCpw) load_chunk(tt, c + 2, sA, vA);
+          if (cc + 2 < kCpw) {
+            load_chunk(tt, c + 2, sA, vA);
+          } else if (TC_KNOCK(128) && tt + 1 < my_tiles) {
+            // staged for round 2: one warp-uniform poll of the next tile's barriers (tcgen05.ld is .sync.aligned: all lanes
+            // or none); if S and V are there its first chunk load overlaps this tile's last chunk and hand-off
+            const uint32_t n1 = tt + 1;
+            const bool ready = ptx::mbar_try_wait(BAR(B_VFULL + n1 % NV), (n1 / NV) & 1) &&
+                               ptx::mbar_try_wait(BAR(B_SFULL + n1 % NS), (n1 / NS) & 1);
+            if (__all_sync(0xffffffffu, ready)) {
+              ptx::tc_fence_after();
+              load_chunk(n1, c_lo, sA, vA);
+              started = true;
+            }
+          }
           compute_chunk(tt, c + 1, sB, vB);
         }
         ptx::tc_wait_st();

@@ -3,6 +3,8 @@
 Skips one pipeline stage at a time (results are invalid) to see which stage bounds the kernel:
   1 no MUFU reciprocal | 2 no V shared-memory reads | 4 ratio = TMEM load + store only | 8 no O-MMA | 16 no S-MMA |
   32 no V TMA loads (no HBM stream)
+Staged variants with VALID results (A/B them inside one gpurun call): 64 a quarter of the reciprocals on the FMA pipe |
+  128 start the next tile's first chunk load before this tile's last chunk
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,7 +17,8 @@ N, C, R = 65536, 4096, 64
 torch.manual_seed(0)
 V = torch.rand(N, C, device="cuda").bfloat16().float()
 W = torch.randn(C, R, device="cuda").abs(); H = torch.randn(N, R, device="cuda").abs()
-for k in [0, 1, 2, 3, 4, 8, 16, 24, 32, 33, 35, 36, 40, 56, 60, 63]:
+ks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4, 8, 16, 24, 32, 33, 35, 36, 40, 56, 60, 63, 0, 64, 128, 192, 0]
+for k in ks:
     os.environ["NMFB200_TC_KNOCK"] = str(k)       # read once per engine context
     eng = CudaNmfEngine(V, W, H, prec)
     out = []
