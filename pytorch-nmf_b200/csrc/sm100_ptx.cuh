@@ -39,6 +39,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires instead of
+// returning after a few tens of cycles (CUTLASS passes the same 0x989680).  Staged for round 2 behind NMFB200_TC_PARK in
+// the tuning build: the unparked poll loops execute ~4 M try_wait per launch (ncu source page), a quarter of the SM's
+// issue slots and avoidable power on a power-capped part; one cross-box measurement showed no gain.
+__device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+#ifdef NMFB200_TRACE
+__device__ unsigned int g_tune_park;      // tuning build: non-zero = parked polls in mbar_wait_slow
+#endif
 // Bounded wait: on a protocol bug (no progress for ~1 s) the first waiter records (block, thread, barrier, parity)
 // in g_wait_abort and every wait in the grid then falls through, so the kernel terminates instead of hanging
 // the GPU box; the host checks the record after the launch (tc_nmf.cu: check_wait_abort).
@@ -51,7 +69,12 @@ __device__ unsigned int g_wait_abort[8];
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
+#ifdef NMFB200_TRACE
+  const bool park = *reinterpret_cast<volatile unsigned int*>(&g_tune_park) != 0u;
+#else
+  constexpr bool park = false;
+#endif
+  while (!(park ? mbar_try_wait_parked(bar, parity) : mbar_try_wait(bar, parity))) {
     if ((++polls & 1023u) != 0u) continue;
     if (*reinterpret_cast<volatile unsigned int*>(&g_wait_abort[0]) != 0u) return;
     const long long now = clock64();

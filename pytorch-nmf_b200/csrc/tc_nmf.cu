@@ -1268,7 +1268,7 @@ struct TcState {
   // Environment knobs, read once in tc_create.  Product build: NMFB200_CENTER=0 (diagnostic: kappa centring off, see
   // tools/bias_probe.py), NMFB200_GRAPH=1 (CUDA-graph replay of tc_iterate), NMFB200_TC_CHECK=1 (watchdog check after
   // every tc_contract_only).  Tuning build (-DNMFB200_TRACE) only: NMFB200_TC_VARIANT, NMFB200_TC_PF, NMFB200_TC_KNOCK,
-  // NMFB200_TC_TRACE=<file>.
+  // NMFB200_TC_PARK, NMFB200_TC_TRACE=<file>.
   int center = 1;
   bool use_graph = false, check_each = false;
   int pf_dist = 0;                  // L2 prefetch distance of the V stream in tiles (measured: no gain; 0 = off)
@@ -1316,6 +1316,10 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (const char* e = getenv("NMFB200_TC_VARIANT")) s->variant = atoi(e);
   if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
   if (const char* e = getenv("NMFB200_TC_KNOCK")) s->knock = atoi(e);
+  {
+    const unsigned int park = getenv("NMFB200_TC_PARK") ? 1u : 0u;        // parked mbarrier polls (staged variant)
+    cudaMemcpyToSymbol(ptx::g_tune_park, &park, sizeof(park));
+  }
   if (const char* e = getenv("NMFB200_TC_TRACE")) {
     s->trace_path = e;
     if (cudaMalloc(&s->trace, 256 * 12 * sizeof(long long)) != cudaSuccess) s->trace = nullptr;
