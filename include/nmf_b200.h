@@ -55,12 +55,17 @@ typedef struct nmfb200_ctx nmfb200_ctx;
 
 int         nmfb200_abi_version(void);
 const char* nmfb200_last_error(void);
+/* "src=<sha256/16 of csrc/* + this header> nvcc=<version> arch=sm_100a built=<date time>": which sources this binary is */
+const char* nmfb200_build_info(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t     nmfb200_launch_count(void);
 
 /* Synchronises `stream` and reports whether any kernel of this library aborted an internal wait (a protocol
  * bug or a wedged device): 0 = healthy, non-zero = the results since the last check are invalid. */
 int nmfb200_check_health(void* stream);
+/* Same, on the context's device (the plain form looks at whichever device is current); the caller's current device is
+ * left unchanged, as it is by every entry point that takes a context. */
+int nmfb200_ctx_check_health(nmfb200_ctx* ctx, void* stream);
 
 /* ---- dense NMF ------------------------------------------------------------------------- */
 

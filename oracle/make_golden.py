@@ -143,13 +143,89 @@ def cfg2_case(iters=200):
     print("wrote nmf_cfg2_kl_200.npz")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Round 2: goldens at the shapes of BASELINE.json configs[2..4] (kernel paths the small cases never reach).
+# Inputs are regenerated from seeds by the tests (checksums stored); only subsampled factors are stored.
+# ---------------------------------------------------------------------------------------------------------
+def _store(flat, name, V, W0, H0, W, H, n_iter, losses, meta, w_step=1, h_step=1):
+    flat[f"{name}/W_sub"] = W[::w_step].numpy()
+    flat[f"{name}/H_sub"] = (H[::h_step] if H.dim() == 2 else H).numpy()
+    flat[f"{name}/w_step"] = np.array(w_step); flat[f"{name}/h_step"] = np.array(h_step)
+    flat[f"{name}/n_iter"] = np.array(n_iter)
+    flat[f"{name}/losses"] = np.array(losses, dtype=np.float64)
+    flat[f"{name}/v_sum"] = np.array(V.double().sum().item())
+    flat[f"{name}/w0_sum"] = np.array(W0.double().sum().item())
+    flat[f"{name}/h0_sum"] = np.array(H0.double().sum().item())
+    flat[f"{name}/w_absmax"] = np.array(W.abs().max().item())
+    flat[f"{name}/h_absmax"] = np.array(H.abs().max().item())
+    for k, v in meta.items():
+        flat[f"{name}/{k}"] = np.array(v, dtype=np.float64)
+
+
+def heavy_tailed(N, C, seed=0):
+    """Spectrogram-like target: lognormal magnitudes over ~6 decades (exercises the fp16 range handling)."""
+    torch.manual_seed(seed)
+    return torch.exp(2.0 * torch.randn(N, C)).bfloat16().float()
+
+
+def round2_cases():
+    torch.set_num_threads(os.cpu_count())
+    torch.set_flush_denormal(True)
+    flat = {}
+    # --- cfg3: NMFD spectrogram 1025 x 8192, R = 16, T = 128, beta = 1, 20 iterations (reference ~0.8 s / iteration) ---
+    t0 = time.time()
+    B, C, L, R, T = 1, 1025, 8192, 16, 128
+    V, W0, H0 = make_inputs((B, C, L), (C, R, T), (B, R, L - T + 1))
+    W, H, n_iter, losses = run_reference(ref_nmf.NMFD, V, W0, H0, 1, float("-inf"), 20, 0, 0)
+    _store(flat, "nmfd_cfg3", V, W0, H0, W, H, n_iter, losses,
+           dict(B=B, C=C, L=L, R=R, T=T, beta=1, max_iter=20), w_step=8)
+    print(f"nmfd_cfg3 {time.time() - t0:.1f}s", flush=True)
+    # --- NMFD ragged: T = 37 crosses the 32-wide shift chunk, C = 130 crosses the 128-row tile, batch 2 ---
+    B, C, L, R, T = 2, 130, 700, 5, 37
+    for beta in (1, 0.5):
+        V, W0, H0 = make_inputs((B, C, L), (C, R, T), (B, R, L - T + 1))
+        W, H, n_iter, losses = run_reference(ref_nmf.NMFD, V, W0, H0, beta, float("-inf"), 20, 0, 0)
+        _store(flat, f"nmfd_ragged_b{beta}", V, W0, H0, W, H, n_iter, losses,
+               dict(B=B, C=C, L=L, R=R, T=T, beta=beta, max_iter=20))
+    print(f"nmfd_ragged {time.time() - t0:.1f}s", flush=True)
+    # --- cfg4-shaped: R = 128 (the 128-column operand kernels), KL, 100 iterations ---
+    N, C, R = 8192, 2048, 128
+    V, W0, H0 = make_inputs((N, C), (C, R), (N, R))
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, 1, float("-inf"), 100, 0, 0)
+    _store(flat, "nmf_r128_kl", V, W0, H0, W, H, n_iter, losses, dict(N=N, C=C, R=R, beta=1, max_iter=100), h_step=8)
+    print(f"nmf_r128 {time.time() - t0:.1f}s", flush=True)
+    # --- cfg5-shaped: beta sweep at R = 64, 50 iterations ---
+    N, C, R = 4096, 1024, 64
+    for beta in (0, 0.5, 1.5, 2):
+        V, W0, H0 = make_inputs((N, C), (C, R), (N, R), floor=2 ** -7 if beta <= 0 else 0.0)
+        W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, beta, float("-inf"), 50, 0, 0)
+        _store(flat, f"nmf_sweep_b{beta}", V, W0, H0, W, H, n_iter, losses,
+               dict(N=N, C=C, R=R, beta=beta, max_iter=50, floor=2 ** -7 if beta <= 0 else 0.0), h_step=4)
+    print(f"sweep {time.time() - t0:.1f}s", flush=True)
+    # --- heavy-tailed targets (lognormal, ~6 decades): KL and IS, 30 iterations ---
+    N, C, R = 1024, 512, 32
+    for beta in (1, 0):
+        V = heavy_tailed(N, C)
+        torch.manual_seed(1)
+        W0 = torch.randn(C, R).abs(); H0 = torch.randn(N, R).abs()
+        W, H, n_iter, losses = run_reference(ref_nmf.NMF, V, W0, H0, beta, float("-inf"), 30, 0, 0)
+        _store(flat, f"nmf_heavy_b{beta}", V, W0, H0, W, H, n_iter, losses,
+               dict(N=N, C=C, R=R, beta=beta, max_iter=30))
+    np.savez_compressed(os.path.join(GOLD, "reference_r2.npz"), **flat)
+    print(f"wrote reference_r2.npz ({os.path.getsize(os.path.join(GOLD, 'reference_r2.npz')) / 1e6:.2f} MB) in {time.time() - t0:.1f}s")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg2", action="store_true")
     ap.add_argument("--only-cfg2", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--r2", action="store_true", help="only the round-2 fixtures (reference_r2.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.r2:
+        round2_cases()
+        sys.exit(0)
     if not a.only_cfg2:
         save_cases(small_cases(), "reference_small.npz")
     if a.cfg2 or a.only_cfg2:

@@ -31,6 +31,18 @@ def _nvcc():
     raise RuntimeError("nvcc not found; cannot build libnmf_b200.so")
 
 
+def source_hash():
+    """sha256 over every file the library is compiled from (csrc/*, include/nmf_b200.h), first 16 hex digits.  Compiled
+    into the library (nmfb200_build_info) so a test can prove the .so on the GPU box was built from these sources."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "nmf_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
@@ -46,11 +58,12 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
+    stamp = source_hash()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        cmd = [nvcc] + NVCC_FLAGS + [f'-DNMFB200_SRC_HASH="{stamp}"'] + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -39,6 +39,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (try_wait may suspend the thread until the phase completes or a time limit expires)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires instead of
 // returning after a few tens of cycles (CUTLASS passes the same 0x989680).  Staged for round 2 behind NMFB200_TC_PARK in
 // the tuning build: the unparked poll loops execute ~4 M try_wait per launch (ncu source page), a quarter of the SM's
@@ -237,6 +249,25 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2, two fp32 lanes per 64-bit register pair and per issue slot) ---------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 // {lo, hi} fp32 -> packed f16x2 (lo in bits 0-15), round-to-nearest, saturating to the largest finite half
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {

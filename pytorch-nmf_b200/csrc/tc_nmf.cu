@@ -21,6 +21,7 @@
 // pipe, across work-item boundaries.
 #include "tc_nmf.cuh"
 
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -381,10 +382,13 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     uint32_t t = 0;
     const float vinv = exp2f(-(float)ev);
     if constexpr (!LOSS && !TWO) {
-      // ---- update tiles of beta 1 / beta 2: one flat loop over this CTA's tiles, software-pipelined over 16-column chunks:
-      // the TMEM load of S and the shared-memory load of V for chunk c + 1 are in flight while chunk c is computed.
-      // (Also tried, no gain on the B200: starting the next tile's first chunk before the last chunk of this tile is
-      // computed; FMA-pipe reciprocals for a quarter of the elements; parked try_wait.  DESIGN.md 4.1.)
+      // ---- update tiles of beta 1 / beta 2: ONE flat software pipeline over every (tile, 16-column chunk) of this CTA.
+      // * the TMEM load of S and the shared-memory load of V for chunk c + 1 are in flight while chunk c is computed, across
+      //   tile boundaries: the next tile's barriers are polled (try_wait issued early, predicate consumed after a chunk of
+      //   math) and its first chunk requested before this tile's last chunk is computed;
+      // * reciprocals are batched four elements to two MUFU ops (1/a = b * rcp(a b)): the XU pipe (16 results per clock
+      //   and SM) was the busiest unit of the round-1 kernel at one reciprocal per element; everything else runs as packed
+      //   fp32 pairs (FFMA2 / FMUL2), half the issue slots of scalar FFMA.
       constexpr int kChunks = TN / 16;
       constexpr int kCpw = kChunks / NRW;                       // chunks per warpgroup and tile
       static_assert(kCpw % 2 == 0 && kChunks % NRW == 0, "chunks per ratio warpgroup");
@@ -394,6 +398,8 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const int tb = (item / p.row_blocks) * p.tiles_per_chunk;
         my_tiles += min(p.tiles, tb + p.tiles_per_chunk) - tb;
       }
+      const uint64_t C1 = ptx::pk2(c1, c1), C2 = ptx::pk2(c2, c2), NEGPC = ptx::pk2(negpc, negpc);
+      const uint64_t EUCV = ptx::pk2(eu_cv, eu_cv), EUNCS = ptx::pk2(-eu_cs, -eu_cs);
       uint32_t sA[16], sB[16];
       uint4 vA[2], vB[2];
       auto load_chunk = [&](uint32_t tile, int c, uint32_t (&sr)[16], uint4 (&vv)[2]) {
@@ -412,71 +418,76 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         const uint32_t* vw = reinterpret_cast<const uint32_t*>(vv);
         uint32_t preg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vw[i]));
-          float p0, p1;
+        for (int qd = 0; qd < 4; ++qd) {                         // four consecutive columns: pairs a = (0, 1), b = (2, 3)
+          const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&vw[2 * qd]));
+          const float2 vb = __half22float2(*reinterpret_cast<const __half2*>(&vw[2 * qd + 1]));
+          const uint64_t Sa = ptx::pk2(__uint_as_float(sr[4 * qd]), __uint_as_float(sr[4 * qd + 1]));
+          const uint64_t Sb = ptx::pk2(__uint_as_float(sr[4 * qd + 2]), __uint_as_float(sr[4 * qd + 3]));
+          uint64_t Pa, Pb;
           if (EU) {
-            p0 = fmaf(vf.x, eu_cv, -__uint_as_float(sr[2 * i]) * eu_cs);            // nmf.py:62-63: V - WH
-            p1 = fmaf(vf.y, eu_cv, -__uint_as_float(sr[2 * i + 1]) * eu_cs);
+            Pa = ptx::fma2(Sa, EUNCS, ptx::mul2(ptx::pk2(va.x, va.y), EUCV));     // nmf.py:62-63: V - kappa WH
+            Pb = ptx::fma2(Sb, EUNCS, ptx::mul2(ptx::pk2(vb.x, vb.y), EUCV));
           } else {
-            const float x0 = fmaf(__uint_as_float(sr[2 * i]), c1, c2);
-            const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), c1, c2);
-            // (tuning build, bit 64: every fourth pair takes its reciprocals on the FMA pipe -- valid results)
-            const bool on_fma = TC_KNOCK(64) && (i & 3) == 3;
-            const float r0 = on_fma ? ptx::rcp_fma(x0) : ptx::rcp_approx(x0);
-            const float r1 = on_fma ? ptx::rcp_fma(x1) : ptx::rcp_approx(x1);
-            p0 = fmaf(vf.x, TC_KNOCK(1) ? x0 : r0, negpc);                          // nmf.py:65, centred
-            p1 = fmaf(vf.y, TC_KNOCK(1) ? x1 : r1, negpc);
+            const uint64_t Xa = ptx::fma2(Sa, C1, C2), Xb = ptx::fma2(Sb, C1, C2);   // (WH + eps) in the scale of V~ / P~
+            float m0, m1;
+            ptx::upk2(ptx::mul2(Xa, Xb), m0, m1);
+            const float r0 = TC_KNOCK(1) ? m0 : ptx::rcp_approx(m0);                // 1 / (x0 x2), 1 / (x1 x3)
+            const float r1 = TC_KNOCK(1) ? m1 : ptx::rcp_approx(m1);
+            const uint64_t Rr = ptx::pk2(r0, r1);
+            // 1 / x0 = x2 r0, 1 / x1 = x3 r1 (pair a);  1 / x2 = x0 r0, 1 / x3 = x1 r1 (pair b)
+            Pa = ptx::fma2(ptx::pk2(va.x, va.y), ptx::mul2(Rr, Xb), NEGPC);         // nmf.py:65, centred
+            Pb = ptx::fma2(ptx::pk2(vb.x, vb.y), ptx::mul2(Rr, Xa), NEGPC);
           }
-          preg[i] = TC_KNOCK(4) ? sr[i] : ptx::pack_f16x2_sat(p0, p1);
+          float a0, a1, b0, b1;
+          ptx::upk2(Pa, a0, a1);
+          ptx::upk2(Pb, b0, b1);
+          preg[2 * qd] = TC_KNOCK(4) ? sr[2 * qd] : ptx::pack_f16x2_sat(a0, a1);
+          preg[2 * qd + 1] = TC_KNOCK(4) ? sr[2 * qd + 1] : ptx::pack_f16x2_sat(b0, b1);
         }
         // P of warpgroup g goes over the S columns that warpgroup owns (and has already read): [g TN / NRW, ...)
         ptx::tmem_st8(tmem + lane_addr + kColS + (tile % NS) * TN + g * (TN / NRW) + (c - c_lo) * 8, preg);
       };
-      bool started = false;      // tuning build, bit 128: the first chunk of this tile was requested during the previous one
+      if (my_tiles > 0) {
+        if (q == 0 && lane == 0) TC_TRACE(0, 2);
+        ptx::mbar_wait(BAR(B_VFULL), 0);                            // V tile landed (TMA -> this thread)
+        ptx::mbar_wait(BAR(B_SFULL), 0);                            // S tile complete
+        if (q == 0 && lane == 0) TC_TRACE(0, 4);
+        ptx::tc_fence_after();
+        load_chunk(0, c_lo, sA, vA);
+      }
       for (uint32_t tt = 0; tt < my_tiles; ++tt) {
-        const uint32_t s = tt % NV, st = tt % NS;
-        if (!started) {
-          if (q == 0 && lane == 0) TC_TRACE(tt, 2);
-          ptx::mbar_wait(BAR(B_VFULL + s), (tt / NV) & 1);        // V tile landed (TMA -> this thread)
-          if (q == 0 && lane == 0) TC_TRACE(tt, 3);
-          ptx::mbar_wait(BAR(B_SFULL + st), (tt / NS) & 1);       // S tile complete
-          if (q == 0 && lane == 0) TC_TRACE(tt, 4);
-          ptx::tc_fence_after();
-          load_chunk(tt, c_lo, sA, vA);
-        }
-        started = false;
+        const uint32_t n1 = tt + 1;
+        const bool more = n1 < my_tiles;
 #pragma unroll
         for (int cc = 0; cc < kCpw; cc += 2) {
           const int c = c_lo + cc;
+          const bool lastpair = cc + 2 >= kCpw;
+          bool okV = true, okS = true;
+          if (lastpair && more) {                                   // probe early (non-blocking), consume after a chunk of math
+            okV = ptx::mbar_test_wait(BAR(B_VFULL + n1 % NV), (n1 / NV) & 1);
+            okS = ptx::mbar_test_wait(BAR(B_SFULL + n1 % NS), (n1 / NS) & 1);
+          }
           ptx::tc_wait_ld();
           load_chunk(tt, c + 1, sB, vB);
           compute_chunk(tt, c, sA, vA);
           ptx::tc_wait_ld();
-          if (cc + 2 < kCpw) {
+          if (!lastpair) {
             load_chunk(tt, c + 2, sA, vA);
-          } else if (TC_KNOCK(128) && tt + 1 < my_tiles) {
-            // staged for round 2: one warp-uniform poll of the next tile's barriers (tcgen05.ld is .sync.aligned: all lanes
-            // or none); if S and V are there its first chunk load overlaps this tile's last chunk and hand-off
-            const uint32_t n1 = tt + 1;
-            const bool ready = ptx::mbar_try_wait(BAR(B_VFULL + n1 % NV), (n1 / NV) & 1) &&
-                               ptx::mbar_try_wait(BAR(B_SFULL + n1 % NS), (n1 / NS) & 1);
-            if (__all_sync(0xffffffffu, ready)) {
-              ptx::tc_fence_after();
-              load_chunk(n1, c_lo, sA, vA);
-              started = true;
-            }
+          } else if (more) {
+            if (!okV) ptx::mbar_wait_slow(BAR(B_VFULL + n1 % NV), (n1 / NV) & 1);
+            if (!okS) ptx::mbar_wait_slow(BAR(B_SFULL + n1 % NS), (n1 / NS) & 1);
+            if (q == 0 && lane == 0) TC_TRACE(n1, 4);
+            ptx::tc_fence_after();
+            load_chunk(n1, c_lo, sA, vA);
           }
           compute_chunk(tt, c + 1, sB, vB);
         }
+        // hand the tile on at once: the S/P stage and the V slot are what the rings are short of
         ptx::tc_wait_st();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(BAR(B_PFULL + st));
-        ptx::mbar_arrive(BAR(B_VEMPTY + s));
-        // per-warp end times (tuning build): slot 9 = warpgroup 0 / quarter 0, 10 = warpgroup 0 / quarter 3,
-        // 11 = last warpgroup / quarter 3 -- the skew between them is the wait of the O-MMA on the 256 p_full arrivals
+        ptx::mbar_arrive(BAR(B_PFULL + tt % NS));
+        ptx::mbar_arrive(BAR(B_VEMPTY + tt % NV));
         if (lane == 0 && g == 0 && q == 0) TC_TRACE(tt, 9);
-        if (lane == 0 && g == 0 && q == 3) TC_TRACE(tt, 10);
         if (lane == 0 && g == NRW - 1 && q == 3) TC_TRACE(tt, 11);
       }
     } else {
@@ -726,6 +737,34 @@ __device__ __forceinline__ int pow2_exp_for(float mx) {
   return 14 - e;
 }
 
+// What the last stage of a factor refresh publishes (one thread): the operand exponent of this factor, kappa =
+// sum(V) / sum(W H^T) = sum(V) / <colsum W, colsum H> (the typical P = V / (WH)), the ratio-tile exponent exps[3] with
+// kappa 2^p in [2^-4, 2^-3) (P - kappa is fp16-exact down to 2^-20 kappa, and a ratio has to exceed 5e5 kappa before the
+// saturating pack clips it), and the exponents of the beta != 1 tiles.
+__device__ __forceinline__ void publish_scales(int a, int which, int* __restrict__ exps, unsigned int* __restrict__ absmax_next,
+                                               float dot, const double* __restrict__ vconst, float* __restrict__ kappa,
+                                               int center, float bm1, float bm2, double cells) {
+  exps[1 + which] = a;
+  *absmax_next = 0u;
+  const float ptyp = (float)(vconst[0] / (double)dot);
+  int e = 0;
+  const bool ok = ptyp > 0.f && isfinite(ptyp);
+  if (ok) { frexpf(ptyp, &e); e = -3 - e; }     // ptyp * 2^e in [2^-4, 2^-3)
+  exps[3] = e;
+  *kappa = (ok && center) ? ptyp : 0.f;
+  // beta != 1: typical x = mean(WH), typical Pn = mean(V) x^(beta-2), Pp = x^(beta-1) -> both tiles near 2^0
+  const float xbar = (float)((double)dot / cells), vbar = (float)(vconst[0] / cells);
+  int en = 0, ed = 0;
+  if (xbar > 0.f && isfinite(xbar)) {
+    const float lx = log2f(xbar);
+    const float ln = (vbar > 0.f ? log2f(vbar) : 0.f) + bm2 * lx, ld = bm1 * lx;
+    if (isfinite(ln)) en = -(int)rintf(ln);
+    if (isfinite(ld)) ed = -(int)rintf(ld);
+  }
+  exps[4] = en;
+  exps[5] = ed;
+}
+
 __global__ void set_vexp_kernel(const float* __restrict__ minmax, int* __restrict__ exps) {
   if (threadIdx.x == 0 && blockIdx.x == 0) exps[0] = pow2_exp_for(minmax[1]);
 }
@@ -747,12 +786,14 @@ __device__ __forceinline__ double block_sum256(double v, double* sh) {
 // Also per-block partial sums of V and V*log(V+eps) (the V-only terms of metrics.kl_div, metrics.py:22).
 __global__ void __launch_bounds__(256)
 v_to_f16_kernel(const float* __restrict__ V, int64_t ldv, int N, int C, __half* __restrict__ V16, int64_t ldc,
-                __half* __restrict__ Vt16, int64_t ldn, const int* __restrict__ exps, double* __restrict__ vpart) {
+                __half* __restrict__ Vt16, int64_t ldn, const int* __restrict__ exps, double* __restrict__ vpart,
+                unsigned long long* __restrict__ lossy) {
   __shared__ float tile[64][65];
   __shared__ double red[8];
   const float sc = exp2f((float)exps[0]);
   const int n0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   double sv = 0.0, svl = 0.0;
+  unsigned int nlossy = 0;      // positive entries below the fp16 normal range of the scaled copy (subnormal or flushed)
   for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
     int r = idx >> 6, c = idx & 63;
     const bool in = n0 + r < N && c0 + c < C;
@@ -761,6 +802,7 @@ v_to_f16_kernel(const float* __restrict__ V, int64_t ldv, int N, int C, __half* 
     tile[r][c] = v;
     if (in) {
       V16[(int64_t)(n0 + r) * ldc + c0 + c] = __float2half_rn(v);
+      nlossy += (raw > 0.f && v < 6.103515625e-05f) ? 1u : 0u;
       sv += (double)raw;
       svl += (double)(raw * logf(raw + kEps));
     }
@@ -774,6 +816,8 @@ v_to_f16_kernel(const float* __restrict__ V, int64_t ldv, int N, int C, __half* 
   double a = block_sum256(sv, red);
   double b = block_sum256(svl, red);
   if (threadIdx.x == 0) { vpart[2 * blk] = a; vpart[2 * blk + 1] = b; }
+  nlossy = __reduce_add_sync(0xffffffffu, nlossy);
+  if ((threadIdx.x & 31) == 0 && nlossy) atomicAdd(lossy, (unsigned long long)nlossy);
 }
 
 // vconst[0] = sum V, vconst[1] = sum V log(V + eps): fixed-order two-level reduction (single block)
@@ -1089,36 +1133,162 @@ tc_finish_kernel(const float* __restrict__ x, int64_t rows, int R, __half* __res
       __syncthreads();
       if (threadIdx.x == 0) {
         *ticket = 0u;
-        exps[1 + which] = a;
-        *absmax_next = 0u;
         float dot = 0.f;
         for (int k = 0; k < 128; ++k) dot += prod[k];
-        const float ptyp = (float)(vconst[0] / (double)dot);
-        int e = 0;
-        const bool ok = ptyp > 0.f && isfinite(ptyp);
-        if (ok) { frexpf(ptyp, &e); e = 1 - e; }     // ptyp * 2^e in [1, 2)
-        exps[3] = e;
-        *kappa = (ok && center) ? ptyp : 0.f;
-        // beta != 1: typical x = mean(WH), typical Pn = mean(V) x^(beta-2), Pp = x^(beta-1) -> both tiles near 2^0
-        const float xbar = (float)((double)dot / cells), vbar = (float)(vconst[0] / cells);
-        int en = 0, ed = 0;
-        if (xbar > 0.f && isfinite(xbar)) {
-          const float lx = log2f(xbar);
-          const float ln = (vbar > 0.f ? log2f(vbar) : 0.f) + bm2 * lx, ld = bm1 * lx;
-          if (isfinite(ln)) en = -(int)rintf(ln);
-          if (isfinite(ld)) ed = -(int)rintf(ld);
-        }
-        exps[4] = en;
-        exps[5] = ed;
+        publish_scales(a, which, exps, absmax_next, dot, vconst, kappa, center, bm1, bm2, cells);
       }
     }
   }
 }
 
+// ---- ratio stage + operand refresh in ONE cooperative kernel (R % 4 == 0; beta != 2) ------------------------------------
+// Phase 1 = tc_apply_vec4_kernel (nmf.py:78-92 in place, per-block column sums, global max); grid barrier; phase 2 = the
+// fp16 operand copy with the exponent from that max (rows re-read from L2), while block 0 folds the column sums in fixed
+// order and publishes colsum / kappa / exponents.  Replaces two launches, one pass over the factor and the ticket
+// protocol of tc_finish_kernel; the W side also gets 2 x #SM blocks instead of rows / 64.
+struct TcFinishArgs {
+  __half* out; int KW, Rp;
+  unsigned int* absmax; unsigned int* absmax_next;
+  int* exps; int which;
+  float* colsum; const double* vconst; float* kappa; int center;
+  float bm1, bm2; double cells;
+};
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-add_rowvec_kernel(float* __restrict__ x, int64_t n, int R, const float* __restrict__ v, const float* __restrict__ kappa) {
+tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
+  __shared__ float4 sh[256];
+  const int lanes = a.R >> 2;                    // threads per row
+  const int rows_per_pass = 256 / lanes;
+  const int rl = threadIdx.x / lanes, q = threadIdx.x - rl * lanes;      // row slot, rank quad
+  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
+  const int64_t row1 = min(a.rows, row0 + a.rpb);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  float mx = 0.f;
+  if (rl < rows_per_pass) {
+    float4 kd = make_float4(1.f, 1.f, 1.f, 1.f);
+    float kap = 0.f;
+    if (a.apply && !a.den) { kd = *reinterpret_cast<const float4*>(a.kl_den + 4 * q); kap = *a.kappa; }
+    for (int64_t row = row0 + rl; row < row1; row += rows_per_pass) {
+      float4* pp = reinterpret_cast<float4*>(a.param + row * a.R) + q;
+      float4 v = *pp;
+      if (a.apply) {
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * a.Rp) + q);
+          num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
+        }
+        float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.den) {
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            const float4 t = *(reinterpret_cast<const float4*>(a.den + ch * a.chunk_stride + row * a.Rp) + q);
+            dsum.x += t.x; dsum.y += t.y; dsum.z += t.z; dsum.w += t.w;
+          }
+        }
+        float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
+        const float ds[4] = {dsum.x, dsum.y, dsum.z, dsum.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float n = a.den ? nn[i] : fmaf(kap, dd[i], nn[i]);  // beta == 1: the kernel accumulated sum (P - kappa) G
+          const float neg = fmaxf(n, 0.f) + kEps;                   // nmf.py:78
+          float pos = a.den ? fmaxf(ds[i], 0.f) + kEps : dd[i];     // nmf.py:83 | nmf.py:368-369 / :381-382
+          if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
+          if (a.l2 > 0.f) pos = fmaf(a.l2, vv[i], pos);             // nmf.py:87-88
+          float mult = neg / pos;                                   // nmf.py:89
+          if (a.gamma != 1.0f) mult = powf(mult, a.gamma);          // nmf.py:90-91
+          vv[i] *= mult;                                            // nmf.py:92
+        }
+        v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        *pp = v;
+      }
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+      mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+  }
+  sh[threadIdx.x] = cs;
+  __syncthreads();
+  if (threadIdx.x < lanes) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rows_per_pass; ++k) {
+      const float4 u = sh[k * lanes + threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    *(reinterpret_cast<float4*>(a.cs_part + (int64_t)blockIdx.x * 128) + threadIdx.x) = t;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(f.absmax, __float_as_uint(mx));
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+
+  // ---- phase 2: fp16 operand copy of this block's rows (just written: L2 hits), scaled by 2^a from the global max
+  const int ae = pow2_exp_for(__uint_as_float(*reinterpret_cast<volatile unsigned int*>(f.absmax)));
+  const float sc = exp2f((float)ae);
+  if (rl < rows_per_pass) {
+    for (int64_t row = row0 + rl; row < row1; row += rows_per_pass) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(a.param + row * a.R) + q);
+      const float xv[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+      __half2 hi[2], lo[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        hi[i] = __floats2half2_rn(xv[2 * i], xv[2 * i + 1]);
+        const float2 hf = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(xv[2 * i] - hf.x, xv[2 * i + 1] - hf.y);
+      }
+      *reinterpret_cast<uint2*>(f.out + row * f.KW + 4 * q) = *reinterpret_cast<const uint2*>(hi);
+      if (SPLIT) *reinterpret_cast<uint2*>(f.out + row * f.KW + f.Rp + 4 * q) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+  // ---- block 0: column sums in fixed order (two halves of the block list, then their sum), then the scalars
+  if (blockIdx.x == 0) {
+    __shared__ float partg[256];
+    __shared__ float prod[128];
+    const int r = threadIdx.x & 127, g = threadIdx.x >> 7;
+    float acc = 0.f;
+    if (r < a.R)
+      for (int b = g; b < (int)gridDim.x; b += 2) acc += __ldcg(a.cs_part + (int64_t)b * 128 + r);
+    partg[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const float mine = partg[threadIdx.x] + partg[128 + threadIdx.x];
+      if (threadIdx.x < a.R) f.colsum[f.which * a.R + threadIdx.x] = mine;
+      prod[threadIdx.x] = threadIdx.x < a.R ? mine * f.colsum[(1 - f.which) * a.R + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float dot = 0.f;
+      for (int k = 0; k < 128; ++k) dot += prod[k];
+      publish_scales(ae, f.which, f.exps, f.absmax_next, dot, f.vconst, f.kappa, f.center, f.bm1, f.bm2, f.cells);
+    }
+  }
+}
+
+// Row-sharded W update: this rank's contribution to the all-reduce buffer in one pass (was: chunk reduction, D2D copy,
+// row-vector add).  den == nullptr (beta 1): out = [num + kappa colsum_h | colsum_h]; otherwise out = [num | den].
+__global__ void __launch_bounds__(256)
+w_partial_pack_kernel(const float* __restrict__ num, const float* __restrict__ den, int nchunks, int64_t chunk_stride,
+                      int64_t rows, int R, int Rp, const float* __restrict__ colsum_h, const float* __restrict__ kappa,
+                      float* __restrict__ out) {
+  const int64_t CR = rows * R;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) x[i] = fmaf(*kappa, v[i % R], x[i]);
+  if (i < CR) {
+    const int64_t row = i / R;
+    const int r = (int)(i - row * R);
+    const int64_t off = row * Rp + r;
+    float a = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) a += num[ch * chunk_stride + off];
+    out[i] = den ? a : fmaf(*kappa, colsum_h[r], a);
+  } else if (den) {
+    if (i < 2 * CR) {
+      const int64_t j = i - CR;
+      const int64_t row = j / R;
+      const int r = (int)(j - row * R);
+      float a = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) a += den[ch * chunk_stride + row * Rp + r];
+      out[i] = a;
+    }
+  } else if (i < CR + R) {
+    out[i] = colsum_h[i - CR];
+  }
 }
 
 // loss = sum V log(V+eps) - sum V - ln2 * 2^-v * sum v~ lg2(S+eps) + 2^-(aW+aH) * sum S~      (metrics.py:22)
@@ -1245,6 +1415,7 @@ struct TcState {
   double* vpart = nullptr;          // per-block {sum V, sum V log V}
   int64_t vblocks = 0;
   double* vconst = nullptr;         // {sum V, sum V log(V+eps)}
+  unsigned long long* vlossy = nullptr;   // positive target entries the scaled fp16 copy cannot hold at full precision
   double* loss_part = nullptr;      // [num_sms][2]
   const float* Vsrc = nullptr;      // the registered fp32 target (borrowed) for the V-only loss terms
   int64_t ldv = 0;
@@ -1278,6 +1449,8 @@ struct TcState {
   std::string trace_path;
   float* kappa = nullptr;           // device scalar
   float* zero = nullptr;            // device scalar 0 (kappa of an already complete numerator)
+  int coop_blocks = 0;              // co-resident blocks of the fused tail kernel (cooperative launch), 0 = unavailable
+  bool fused_tail = false;          // ratio stage + operand refresh in one cooperative kernel (NMFB200_FUSED_TAIL=0: two kernels)
 };
 
 bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
@@ -1290,15 +1463,14 @@ static void drop_graphs(TcState* s) {
 }
 
 void tc_destroy(TcState* s) {
-  if (!s) return;
-  cudaSetDevice(s->device);
+  if (!s) return;      // the caller (capi.cu: free_ctx) has selected s->device
   drop_graphs(s);
   if (s->gstream) cudaStreamDestroy(s->gstream);
   if (s->gev_in) cudaEventDestroy(s->gev_in);
   if (s->gev_out) cudaEventDestroy(s->gev_out);
   cudaFree(s->V16); cudaFree(s->Vt16); cudaFree(s->W16); cudaFree(s->H16); cudaFree(s->part); cudaFree(s->part2); cudaFree(s->gram); cudaFree(s->gram_part);
   cudaFree(s->colsum); cudaFree(s->cs_part); cudaFree(s->cs_super); cudaFree(s->ticket); cudaFree(s->absmax); cudaFree(s->exps);
-  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->zero); cudaFree(s->trace);
+  cudaFree(s->vpart); cudaFree(s->vconst); cudaFree(s->vlossy); cudaFree(s->loss_part); cudaFree(s->vbeta); cudaFree(s->vbeta_part); cudaFree(s->kappa); cudaFree(s->zero); cudaFree(s->trace);
   delete s;
 }
 
@@ -1332,6 +1504,18 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   s->num_sms = prop.multiProcessorCount;
   if (prop.major != 10) { delete s; set_error("the tensor-core path needs an sm_100 device"); return 1; }
   if (s->variant == 1 && split && s->Rp == 64) s->TN = 64;
+  {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    const void* fn = split ? (const void*)tc_apply_finish_kernel<true> : (const void*)tc_apply_finish_kernel<false>;
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) == cudaSuccess && per_sm > 0) {
+      if (per_sm > 2) per_sm = 2;
+      s->coop_blocks = per_sm * s->num_sms;
+      if (s->coop_blocks > 1024) s->coop_blocks = 1024;      // cs_part capacity
+    }
+    const char* e = getenv("NMFB200_FUSED_TAIL");
+    s->fused_tail = s->coop_blocks > 0 && !(e && atoi(e) == 0);
+  }
   s->plan_w = make_plan(C, N, s->num_sms, s->TN);
   s->plan_h = make_plan(N, C, s->num_sms, s->TN);
   int64_t pw = (int64_t)s->plan_w.nchunks * C * s->Rp, ph = (int64_t)s->plan_h.nchunks * N * s->Rp;
@@ -1352,6 +1536,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (e == cudaSuccess) e = cudaMalloc(&s->exps, 8 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->vpart, (size_t)s->vblocks * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->vconst, 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->vlossy, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->num_sms * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->zero, sizeof(float));
@@ -1395,8 +1580,9 @@ int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_d
   set_vexp_kernel<<<1, 32, 0, st>>>(minmax_dev, s->exps);
   NMF_LAUNCH_CHECK();
   dim3 grid((unsigned)ceil_div(s->C, 64), (unsigned)ceil_div(s->N, 64));
+  NMF_CUDA_CHECK(cudaMemsetAsync(s->vlossy, 0, sizeof(unsigned long long), st));
   v_to_f16_kernel<<<grid, 256, 0, st>>>(V, ldv, (int)s->N, (int)s->C, s->V16, s->ldc, s->Vt16, s->ldn, s->exps,
-                                        s->vpart);
+                                        s->vpart, s->vlossy);
   NMF_LAUNCH_CHECK();
   reduce_vconst_kernel<<<1, 256, 0, st>>>(s->vpart, s->vblocks, s->vconst);
   NMF_LAUNCH_CHECK();
@@ -1404,6 +1590,18 @@ int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_d
   s->Vsrc = V; s->ldv = ldv; s->vbeta_for = 1.0;
   drop_graphs(s);
   s->dirty_w = s->dirty_h = true;      // exps[3] depends on sum(V)
+  return 0;
+}
+
+int tc_target_lossy(TcState* s, unsigned long long* count, cudaStream_t st) {
+  NMF_CUDA_CHECK(cudaMemcpyAsync(count, s->vlossy, sizeof(*count), cudaMemcpyDeviceToHost, st));
+  NMF_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int tc_target_sum(TcState* s, double* vsum, cudaStream_t st) {
+  NMF_CUDA_CHECK(cudaMemcpyAsync(vsum, s->vconst, sizeof(double), cudaMemcpyDeviceToHost, st));
+  NMF_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1440,6 +1638,24 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   }
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = reduced ? s->zero : s->kappa;
+  if ((s->R & 3) == 0 && !(apply && beta == 2.0 && !reduced) && s->fused_tail) {
+    // one cooperative launch: ratio stage, grid barrier, operand copy + scalars
+    const int lanes = (int)s->R >> 2, rows_per_pass = 256 / lanes;
+    int64_t g = ceil_div(rows, rows_per_pass);
+    if (g > s->coop_blocks) g = s->coop_blocks;
+    a.rpb = (int)round_up(ceil_div(rows, g), rows_per_pass);
+    const int gblocks = (int)ceil_div(rows, a.rpb);
+    TcFinishArgs f{};
+    f.out = which == 0 ? s->W16 : s->H16; f.KW = s->KW; f.Rp = s->Rp; f.absmax = slot; f.absmax_next = next;
+    f.exps = s->exps; f.which = which; f.colsum = s->colsum; f.vconst = s->vconst; f.kappa = s->kappa;
+    f.center = s->center; f.bm1 = (float)(beta - 1.0); f.bm2 = (float)(beta - 2.0);
+    f.cells = (double)s->N * (double)s->C;
+    void* args[2] = {&a, &f};
+    const void* fn = s->split ? (const void*)tc_apply_finish_kernel<true> : (const void*)tc_apply_finish_kernel<false>;
+    NMF_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gblocks), dim3(256), args, 0, st));
+    count_launch();
+    return 0;
+  }
   if (apply && beta == 2.0 && !reduced) {
     // den_raw = F (G^T G): Gram matrix of the other factor (fp32, fixed-order two-level sum), then the EU ratio stage
     if (!other) { set_error("internal: beta 2 update without the other factor"); return 1; }
@@ -1683,14 +1899,13 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
   if (rc) return rc;
   rc = launch_contract(s, 0, beta, st);
   if (rc) return rc;
+  // one launch packs the all-reduce buffer: numerator (chunk sums, + kappa colsum(H_local) for beta 1, since the kernel
+  // accumulated sum_n (P - kappa) H) followed by colsum(H_local) (beta 1) or the raw denominator (include/nmf_b200.h)
   const int64_t CR = s->C * s->R;
-  rc = reduce_chunks(s->part, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp, partial, st);
-  if (rc) return rc;
-  if (beta != 1.0)      // raw denominator partial follows the numerator (include/nmf_b200.h)
-    return reduce_chunks(s->part2, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp, partial + CR, st);
-  NMF_CUDA_CHECK(cudaMemcpyAsync(partial + CR, s->colsum + s->R, s->R * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // the kernel accumulated sum_n (P - kappa) H: add kappa * colsum(H_local) back
-  add_rowvec_kernel<<<(unsigned)ceil_div(CR, 256), 256, 0, st>>>(partial, CR, (int)s->R, s->colsum + s->R, s->kappa);
+  const int64_t total = beta == 1.0 ? CR + s->R : 2 * CR;
+  w_partial_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+      s->part, beta == 1.0 ? nullptr : s->part2, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp,
+      s->colsum + s->R, s->kappa, partial);
   NMF_LAUNCH_CHECK();
   return 0;
 }

@@ -16,6 +16,10 @@ bool tc_supports_loss(const TcState* s, double beta);
 bool tc_supports_partial(const TcState* s, double beta);
 // minmax_dev: device float[2] = {min(V), max(V)} already queued on `st`
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st);
+// number of positive target entries that the scaled fp16 copy holds only as subnormals / zero (synchronises `st`)
+int tc_target_lossy(TcState* s, unsigned long long* count, cudaStream_t st);
+// sum of the registered target (synchronises `st`)
+int tc_target_sum(TcState* s, double* vsum, cudaStream_t st);
 // the fp32 factor changed outside the tensor-core path: operand copies must be rebuilt before use
 void tc_mark_dirty(TcState* s, bool w, bool h);
 int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,

@@ -21,8 +21,10 @@ _vp, _i64, _dbl, _int = _c.c_void_p, _c.c_int64, _c.c_double, _c.c_int
 SIGNATURES = {
     "nmfb200_abi_version": (_int, []),
     "nmfb200_last_error": (_c.c_char_p, []),
+    "nmfb200_build_info": (_c.c_char_p, []),
     "nmfb200_launch_count": (_i64, []),
     "nmfb200_check_health": (_int, [_vp]),
+    "nmfb200_ctx_check_health": (_int, [_vp, _vp]),
     "nmfb200_nmf_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _int]),
     "nmfb200_destroy": (None, [_vp]),
     "nmfb200_precision": (_int, [_vp]),
@@ -62,10 +64,15 @@ def load():
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(needs nvcc). torchnmf_b200 has no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
+    compat = bool(os.environ.get("NMFB200_LIB")) and bool(os.environ.get("NMFB200_LIB_COMPAT"))
     for name, (res, args) in SIGNATURES.items():
+        if compat and not hasattr(lib, name):       # A/B timing against an older build (tools/ only): newer symbols absent
+            continue
         fn = getattr(lib, name)          # AttributeError here == ABI mismatch
         fn.restype = res
         fn.argtypes = args
+    if compat and not hasattr(lib, "nmfb200_ctx_check_health"):
+        lib.nmfb200_ctx_check_health = lambda ctx, stream: lib.nmfb200_check_health(stream)
     if lib.nmfb200_abi_version() != 1:
         raise NmfB200Error("libnmf_b200.so ABI version mismatch")
     _lib = lib
@@ -76,6 +83,11 @@ def check(rc):
     if rc != 0:
         msg = load().nmfb200_last_error()
         raise NmfB200Error(f"libnmf_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def build_info():
+    """The library's build stamp: source hash, nvcc version, target architecture, build time."""
+    return load().nmfb200_build_info().decode()
 
 
 def launch_count():

@@ -56,6 +56,7 @@ class _CudaEngine:
         self._ctx = ctypes.c_void_p()
         self._loss = None
         self._key = None
+        self._wbuf = None
 
     def _acquire(self, key, create):
         """Take a cached context for `key` or create one with `create(ctx_ref)`."""
@@ -104,7 +105,7 @@ class _CudaEngine:
 
     def check_health(self):
         """Raise if a kernel of the library aborted an internal wait since the last check (synchronises)."""
-        _capi.check(self._lib.nmfb200_check_health(_stream(self.device)))
+        _capi.check(self._lib.nmfb200_ctx_check_health(self._ctx, _stream(self.device)))
 
 
 class CudaNmfEngine(_CudaEngine):
@@ -157,7 +158,9 @@ class CudaNmfEngine(_CudaEngine):
     # --- pieces of the row-sharded W update -------------------------------------------------
     def w_partial(self, beta):
         n = int(self._lib.nmfb200_nmf_w_partial_numel(self._ctx, beta))
-        buf = torch.empty(n, dtype=torch.float32, device=self.device)
+        buf = self._wbuf
+        if buf is None or buf.numel() != n:           # one buffer per engine, reused every iteration
+            buf = self._wbuf = torch.empty(n, dtype=torch.float32, device=self.device)
         _capi.check(self._lib.nmfb200_nmf_w_partial(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(buf),
                                                     _stream(self.device)))
         return buf

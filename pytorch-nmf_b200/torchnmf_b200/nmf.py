@@ -118,17 +118,26 @@ class BaseComponent(torch.nn.Module):
     def _check_target_shape(self, V):
         raise NotImplementedError
 
+    # test hook (tests/oracle_engine.py): an engine class used instead of the CUDA engines, so the host logic of `fit`
+    # can be tested on a GPU-less box.  Deliberately NOT a parameter of `fit`: its signature stays the reference's.
+    _engine_factory = None
+
     @torch.no_grad()
     def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
-            precision="auto", group=None, _engine_factory=None):
+            precision="auto", group=None):
         """Learn the model for `V` by minimising the beta-divergence with multiplicative updates.
 
         Positional arguments, defaults, return value (`n_iter`) and exceptions are those of
         `BaseComponent.fit` in the reference (nmf.py:298-409).  Keyword-only extras:
 
-        precision: "auto" | "f32" | "f16" | "f16_split" -- arithmetic of the contraction kernels
+        precision: "auto" | "f32" | "f16" | "f16_split" -- arithmetic of the contraction kernels ("auto": fp16
+                   tensor-core operands where the target fits their range, fp32 CUDA cores otherwise)
         group:     a torch.distributed process group; V and H are then this rank's ROW shard
                    (rows of V <-> rows of H) and W is replicated; one all-reduce per W update.
+
+        dtype: the kernels keep fp32 master factors and fp32 accumulators.  The reference computes in the module's
+        dtype (nmf.py:214-218); here a float64 / half module (or target) is staged through fp32 copies and the result
+        is written back into the same Parameter storages in their own dtype.
         """
         if V.is_sparse:
             raise NotImplementedError("sparse targets are outside the accelerated hot path; "
@@ -139,24 +148,24 @@ class BaseComponent(torch.nn.Module):
 
         # ---- placement: run on the parameters' CUDA device, or stage host buffers through cuda ----
         staged = False
-        if _engine_factory is None:
+        if self._engine_factory is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("torchnmf_b200.fit needs a CUDA device (sm_100a); there is no CPU fallback")
-            if W.device.type == "cuda":
-                dev = W.device
-                Vd = V.to(dev, non_blocking=True).contiguous()
-                Wd, Hd = W.data, H.data
+            f32 = torch.float32
+            on_gpu = W.device.type == "cuda"
+            dev = W.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
+            Vd = V.to(dev, f32, non_blocking=True).contiguous()
+            if on_gpu and W.dtype == f32 and H.dtype == f32:
+                Wd, Hd = W.data, H.data                       # updated in place, like param.data in the reference
             else:
-                staged = True
-                dev = torch.device("cuda", torch.cuda.current_device())
-                Vd = V.to(dev, non_blocking=True).contiguous()
-                Wd = W.data.to(dev, non_blocking=True).contiguous()
-                Hd = H.data.to(dev, non_blocking=True).contiguous()
+                staged = True                                 # host buffers and / or another dtype: fp32 device copies
+                Wd = W.data.to(dev, f32, non_blocking=True).contiguous()
+                Hd = H.data.to(dev, f32, non_blocking=True).contiguous()
             if not Wd.is_contiguous() or not Hd.is_contiguous():
                 raise ValueError("W and H must be contiguous")
             eng = self._build_engine(Vd, Wd, Hd, precision)
         else:
-            eng = _engine_factory(V, W.data, H.data)
+            eng = self._engine_factory(V, W.data, H.data)
         if group is not None:
             if eng.kind != "nmf":
                 raise NotImplementedError("row sharding is implemented for NMF only (NMFD: replicas only)")

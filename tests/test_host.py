@@ -87,6 +87,18 @@ def test_library_exports_every_declared_symbol():
     assert _capi.load().nmfb200_abi_version() == 1
 
 
+def test_library_was_built_from_these_sources():
+    """The .so that runs (here and, shipped by gpurun, on the GPU box) carries the hash of the sources it was compiled
+    from; a stale or foreign binary fails this test instead of silently passing the parity suite."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("nmf_b200_build", os.path.join(ROOT, "pytorch-nmf_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    info = _capi.build_info()
+    assert f"src={mod.source_hash()} " in info, (info, mod.source_hash())
+    assert "arch=sm_100a" in info and "nvcc=12." in info
+
+
 def test_library_rejects_bad_arguments_without_gpu_work():
     lib = _capi.load()
     ctx = ctypes.c_void_p()
@@ -117,8 +129,8 @@ def test_fit_loop_matches_reference(name):
     c = CASES[name]
     cls, eng = (NMF, OracleNmfEngine) if c["kind"] == "nmf" else (NMFD, OracleNmfdEngine)
     m = cls(W=c["W0"], H=c["H0"], trainable_W=bool(c.get("trainable_W", 1)))
-    n_iter = m.fit(c["V"], c["beta"], c["tol"], int(c["max_iter"]), False, c["alpha"], c["l1_ratio"],
-                   _engine_factory=eng)
+    m._engine_factory = eng            # host-logic test hook (an attribute, not a fit() parameter)
+    n_iter = m.fit(c["V"], c["beta"], c["tol"], int(c["max_iter"]), False, c["alpha"], c["l1_ratio"])
     assert n_iter == c["n_iter"]
     assert torch.allclose(m.W.data, c["W"], rtol=5e-5, atol=1e-7)
     assert torch.allclose(m.H.data, c["H"], rtol=5e-5, atol=1e-7)
@@ -127,18 +139,28 @@ def test_fit_loop_matches_reference(name):
 def test_fit_validation_errors():
     V = torch.rand(12, 9)
     m = NMF(V.shape, 3)
+    m._engine_factory = OracleNmfEngine
     Vneg = V.clone(); Vneg[0, 0] = -1
     with pytest.raises(AssertionError, match="non-negative"):
-        m.fit(Vneg, _engine_factory=OracleNmfEngine)
+        m.fit(Vneg)
     Vz = V.clone(); Vz[0, 0] = 0
     with pytest.raises(ValueError, match="beta <= 0"):
-        m.fit(Vz, beta=0, _engine_factory=OracleNmfEngine)
+        m.fit(Vz, beta=0)
     with pytest.raises(RuntimeError, match="does not match"):
-        m.fit(torch.rand(5, 5), _engine_factory=OracleNmfEngine)
+        m.fit(torch.rand(5, 5))
 
 
 def test_fit_returns_niter_plus_one_and_verbose_runs():
     V = torch.rand(20, 10)
     m = NMF(V.shape, 3)
-    assert m.fit(V, 1, float("-inf"), 7, True, _engine_factory=OracleNmfEngine) == 7
+    m._engine_factory = OracleNmfEngine
+    assert m.fit(V, 1, float("-inf"), 7, True) == 7
     assert not torch.isnan(m.W).any() and not torch.isnan(m.H).any()
+
+
+def test_fit_signature_is_the_references():
+    import inspect
+    sig = inspect.signature(NMF.fit)
+    assert list(sig.parameters)[:8] == ["self", "V", "beta", "tol", "max_iter", "verbose", "alpha", "l1_ratio"]   # nmf.py:298-306
+    extras = [p for p in sig.parameters.values() if p.kind is inspect.Parameter.KEYWORD_ONLY]
+    assert sorted(p.name for p in extras) == ["group", "precision"]

@@ -86,3 +86,50 @@ def test_sharded_w_contractions_sum_to_full():
         n1, d1 = orc.nmf_w_contractions(V[40:], W, H[40:], beta)
         assert torch.allclose(n0 + n1, num, rtol=1e-5, atol=1e-6)
         assert torch.allclose(d0 + d1, den, rtol=1e-5, atol=1e-6)
+
+
+# ---- round-2 fixtures (tests/golden/reference_r2.npz): the oracle at the config shapes --------------------------
+import os  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from conftest import GOLDEN  # noqa: E402
+
+_Z2 = np.load(os.path.join(GOLDEN, "reference_r2.npz"), allow_pickle=False)
+
+
+def _r2_case(name):
+    return {k.split("/", 1)[1]: _Z2[k] for k in _Z2.files if k.startswith(name + "/")}
+
+
+def _r2_inputs(shape_v, shape_w, shape_h, floor=0.0):
+    torch.manual_seed(0)
+    V = torch.rand(*shape_v).bfloat16().float()
+    if floor > 0:
+        V = V.clamp_min(floor)
+    torch.manual_seed(1)
+    return V, torch.randn(*shape_w).abs(), torch.randn(*shape_h).abs()
+
+
+@pytest.mark.parametrize("name", ["nmfd_ragged_b1", "nmfd_ragged_b0.5", "nmf_sweep_b0", "nmf_sweep_b0.5",
+                                  "nmf_sweep_b1.5", "nmf_sweep_b2"])
+def test_oracle_matches_reference_round2_fixtures(name):
+    c = _r2_case(name)
+    torch.set_num_threads(os.cpu_count())
+    if name.startswith("nmfd"):
+        B, C, L, R, T = (int(c[k]) for k in ("B", "C", "L", "R", "T"))
+        V, W0, H0 = _r2_inputs((B, C, L), (C, R, T), (B, R, L - T + 1))
+        kind = "nmfd"
+    else:
+        N, C, R = int(c["N"]), int(c["C"]), int(c["R"])
+        V, W0, H0 = _r2_inputs((N, C), (C, R), (N, R), floor=float(c["floor"]))
+        kind = "nmf"
+    assert math.isclose(V.double().sum().item(), float(c["v_sum"]), rel_tol=1e-12)
+    W, H, n_iter, losses = orc.fit(V, W0, H0, beta=float(c["beta"]), tol=float("-inf"), max_iter=int(c["max_iter"]),
+                                   kind=kind)
+    assert n_iter == int(c["n_iter"])
+    ws, hs = int(c["w_step"]), int(c["h_step"])
+    Hs = H[::hs] if H.dim() == 2 else H
+    # 50 iterations, multi-threaded BLAS on both sides: reduction order differs -> 2e-4
+    assert torch.allclose(W[::ws], torch.from_numpy(c["W_sub"]), rtol=2e-4, atol=1e-6 * float(c["w_absmax"]))
+    assert torch.allclose(Hs, torch.from_numpy(c["H_sub"]), rtol=2e-4, atol=1e-6 * float(c["h_absmax"]))

@@ -44,8 +44,8 @@ def _worker(rank, world, port, beta, alpha, out_dir):
     bounds = [0, 40, N]
     lo, hi = bounds[rank], bounds[rank + 1]
     m = NMF(W=W0, H=H0[lo:hi])
-    n_iter = m.fit(V[lo:hi], beta, 1e-3, 40, False, alpha, 0.5, group=dist.group.WORLD,
-                   _engine_factory=OracleNmfEngine)
+    m._engine_factory = OracleNmfEngine
+    n_iter = m.fit(V[lo:hi], beta, 1e-3, 40, False, alpha, 0.5, group=dist.group.WORLD)
     torch.save({"W": m.W.data, "H": m.H.data, "n_iter": n_iter, "lo": lo, "hi": hi},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
@@ -67,7 +67,8 @@ def test_sharded_fit_equals_single(tmp_path, beta, alpha):
     W0 = torch.randn(C, R).abs()
     H0 = torch.randn(N, R).abs()
     ref = NMF(W=W0, H=H0)
-    n_ref = ref.fit(V, beta, 1e-3, 40, False, alpha, 0.5, _engine_factory=OracleNmfEngine)
+    ref._engine_factory = OracleNmfEngine
+    n_ref = ref.fit(V, beta, 1e-3, 40, False, alpha, 0.5)
     parts = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
     assert all(p["n_iter"] == n_ref for p in parts)          # identical stop decision on every rank
     assert torch.equal(parts[0]["W"], parts[1]["W"])          # W replicas stay bit-identical
