@@ -82,11 +82,14 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;
 #ifdef NMFB200_TRACE
-  const bool park = *reinterpret_cast<volatile unsigned int*>(&g_tune_park) != 0u;
+  const unsigned int mode = *reinterpret_cast<volatile unsigned int*>(&g_tune_park);
+  const bool park = mode == 1u;
 #else
   constexpr bool park = false;
+  constexpr unsigned int mode = 0u;
 #endif
   while (!(park ? mbar_try_wait_parked(bar, parity) : mbar_try_wait(bar, parity))) {
+    if (mode >= 2u) __nanosleep(mode);          // tuning: back-off between polls (issue slots of the spinning warps)
     if ((++polls & 1023u) != 0u) continue;
     if (*reinterpret_cast<volatile unsigned int*>(&g_wait_abort[0]) != 0u) return;
     const long long now = clock64();
