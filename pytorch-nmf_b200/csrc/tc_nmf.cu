@@ -413,7 +413,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       // A "chunk" is CW columns of the tile: the unit of the load / compute software pipeline (the loads of chunk c + 1 are in
       // flight while chunk c is computed).  32-column chunks (twice the lookahead, 126 registers) measured slower than 16
       // (116 / 122 us vs 111 / 118 us per launch at cfg2): the stage is not waiting for its loads.
-      constexpr int CW = 16;
+      constexpr int CW = 16;                                    // tmem_ld16 / tmem_st8 below
       constexpr int kChunks = TN / CW;
       constexpr int kCpw = kChunks / NRW;                       // chunks per warpgroup and tile
       static_assert(kCpw % 2 == 0 && kChunks % NRW == 0, "chunks per ratio warpgroup");
@@ -432,7 +432,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       uint32_t sA[CW], sB[CW];
       uint4 vA[NV4], vB[NV4];
       auto load_chunk = [&](uint32_t tS, uint32_t vT, int c, uint32_t (&sr)[CW], uint4 (&vv)[NV4]) {
-        if constexpr (CW == 32) ptx::tmem_ld32(tS + c * CW, sr); else ptx::tmem_ld16(tS + c * CW, sr);
+        ptx::tmem_ld16(tS + c * CW, sr);
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
           if (TC_KNOCK(2)) { vv[k] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u); continue; }
@@ -486,7 +486,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         // P of warpgroup g goes over the S columns that warpgroup owns (and has already read): [g TN / NRW, ...), or into
         // its k-ordered slice of the tile's own P buffer
         const uint32_t dst = PSEP ? tP + c * (CW / 2) : tS + g * (TN / NRW) + (c - c_lo) * (CW / 2);
-        if constexpr (CW == 32) ptx::tmem_st16(dst, preg); else ptx::tmem_st8(dst, preg);
+        ptx::tmem_st8(dst, preg);
       };
       uint32_t st = 0, sv = 0, phS = 0, phV = 0;        // S stage and V slot of the tile being computed, phases of their full barriers
       uint32_t pb = 0, phP = 0;                         // PSEP: P buffer of the tile being computed, phase of its empty barrier
