@@ -1224,6 +1224,27 @@ struct TcFinishArgs {
   float bm1, bm2; double cells;
 };
 
+// sum over the chunked partial slabs of one float4, four independent loads in flight, fixed summation order
+__device__ __forceinline__ float4 sum_chunks4(const float* __restrict__ p, int nchunks, int64_t stride) {
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ch = 0;
+  for (; ch + 4 <= nchunks; ch += 4) {
+    float4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)(ch + k) * stride));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc[k].x += t[k].x; acc[k].y += t[k].y; acc[k].z += t[k].z; acc[k].w += t[k].w; }
+  }
+  for (; ch < nchunks; ++ch) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)ch * stride));
+    acc[0].x += t.x; acc[0].y += t.y; acc[0].z += t.z; acc[0].w += t.w;
+  }
+  return make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                     (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
@@ -1243,18 +1264,9 @@ tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
       float4* pp = reinterpret_cast<float4*>(a.param + row * a.R) + q;
       float4 v = *pp;
       if (a.apply) {
-        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ch = 0; ch < a.nchunks; ++ch) {
-          const float4 t = *(reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * a.Rp) + q);
-          num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
-        }
-        float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.den) {
-          for (int ch = 0; ch < a.nchunks; ++ch) {
-            const float4 t = *(reinterpret_cast<const float4*>(a.den + ch * a.chunk_stride + row * a.Rp) + q);
-            dsum.x += t.x; dsum.y += t.y; dsum.z += t.z; dsum.w += t.w;
-          }
-        }
+        const float4 num = sum_chunks4(a.num + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride);
+        const float4 dsum = a.den ? sum_chunks4(a.den + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
         const float ds[4] = {dsum.x, dsum.y, dsum.z, dsum.w};
 #pragma unroll
@@ -1312,14 +1324,33 @@ tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
   if (blockIdx.x == 0) {
     __shared__ float partg[256];
     __shared__ float prod[128];
-    const int r = threadIdx.x & 127, g = threadIdx.x >> 7;
-    float acc = 0.f;
-    if (r < a.R)
-      for (int b = g; b < (int)gridDim.x; b += 2) acc += __ldcg(a.cs_part + (int64_t)b * 128 + r);
-    partg[threadIdx.x] = acc;
+    const int fl = a.R <= 32 ? 32 : (a.R <= 64 ? 64 : 128);     // lanes per group; 256 / fl groups walk the block list
+    const int groups = 256 / fl;
+    const int r = threadIdx.x % fl, g = threadIdx.x / fl;
+    // this one block is on the kernel's critical path: 16 loads in flight per thread (an L2 round trip per batch)
+    float acc16[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc16[k] = 0.f;
+    if (r < a.R) {
+      int b = g;
+      for (; b + 15 * groups < (int)gridDim.x; b += 16 * groups) {
+        float t[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t[k] = __ldcg(a.cs_part + (int64_t)(b + k * groups) * 128 + r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc16[k] += t[k];
+      }
+      for (; b < (int)gridDim.x; b += groups) acc16[0] += __ldcg(a.cs_part + (int64_t)b * 128 + r);
+    }
+    float accs = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) accs += acc16[k];
+    partg[threadIdx.x] = accs;
     __syncthreads();
     if (threadIdx.x < 128) {
-      const float mine = partg[threadIdx.x] + partg[128 + threadIdx.x];
+      float mine = 0.f;
+      if (threadIdx.x < fl)
+        for (int k = 0; k < groups; ++k) mine += partg[k * fl + threadIdx.x];
       if (threadIdx.x < a.R) f.colsum[f.which * a.R + threadIdx.x] = mine;
       prod[threadIdx.x] = threadIdx.x < a.R ? mine * f.colsum[(1 - f.which) * a.R + threadIdx.x] : 0.f;
     }
@@ -1581,7 +1612,7 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     const void* fn = split ? (const void*)tc_apply_finish_kernel<true> : (const void*)tc_apply_finish_kernel<false>;
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) == cudaSuccess && per_sm > 0) {
-      if (per_sm > 2) per_sm = 2;
+      if (per_sm > 4) per_sm = 4;                            // enough loads in flight to stream the partials
       s->coop_blocks = per_sm * s->num_sms;
       if (s->coop_blocks > 1024) s->coop_blocks = 1024;      // cs_part capacity
     }
