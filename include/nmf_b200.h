@@ -114,6 +114,14 @@ int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double be
 int64_t nmfb200_nmf_w_partial_numel(const nmfb200_ctx* ctx, double beta);
 int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
                           float* partial, void* stream);
+/* Raw terms of the multiplicative update of ONE factor (which = 0: W, 1: H), computed from the current W and H without
+ * touching either: `out` receives the numerator relu-free (rows*R: the first backward pass of nmf.py:76-78 /
+ * trainer.py:91-93), then colsum(other factor) (R, beta == 1: nmf.py:122-131) or the raw denominator (rows*R: the second
+ * backward pass, nmf.py:82 / trainer.py:95-96).  This is what torchnmf.trainer.BetaMu.step (trainer.py:36-121) and
+ * torchnmf.plca (plca.py:252-253: the simultaneous W / H / Z updates from ONE V / (W Z H) ratio) are built from. */
+int64_t nmfb200_nmf_raw_terms_numel(const nmfb200_ctx* ctx, int which, double beta);
+int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta,
+                          float* out, void* stream);
 int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced,
                         double beta, double gamma, double l1_reg, double l2_reg, void* stream);
 

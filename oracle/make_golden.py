@@ -215,14 +215,73 @@ def round2_cases():
     print(f"wrote reference_r2.npz ({os.path.getsize(os.path.join(GOLD, 'reference_r2.npz')) / 1e6:.2f} MB) in {time.time() - t0:.1f}s")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Round 2, "next" rows: trainer.BetaMu single steps and PLCA fits from the real reference (reference_next.npz)
+# ---------------------------------------------------------------------------------------------------------
+def next_row_cases():
+    import torchnmf.plca as ref_plca
+    import torchnmf.trainer as ref_trainer
+    torch.set_num_threads(1)
+    flat = {}
+    # --- BetaMu: three steps over [W, H] of one NMF module, every beta branch, with l1 / l2 / orthogonal penalties ---
+    N, C, R = 96, 80, 8
+    for beta in (-1, 0, 0.5, 1, 1.5, 2, 3):
+        for tag, (l1, l2, ortho) in (("plain", (0, 0, 0)), ("reg", (0.1, 0.05, 0.2))):
+            torch.manual_seed(0)
+            V = torch.rand(N, C).bfloat16().float() + (2 ** -7 if beta <= 0 else 0.0)
+            torch.manual_seed(1)
+            W0 = torch.randn(C, R).abs(); H0 = torch.randn(N, R).abs()
+            m = ref_nmf.NMF(W=W0, H=H0)
+            tr = ref_trainer.BetaMu([m.W, m.H], beta, l1, l2, ortho)
+
+            def closure():
+                tr.zero_grad()
+                return V, m()
+            for _ in range(3):
+                tr.step(closure)
+            name = f"betamu_b{beta}_{tag}"
+            # (the closure's zero_grad() clears W.grad again before H is updated: only the last parameter keeps its .grad)
+            for k, v in dict(V=V, W0=W0, H0=H0, W=m.W.detach().clone(), H=m.H.detach().clone(),
+                             gH=m.H.grad.clone()).items():
+                flat[f"{name}/{k}"] = v.numpy()
+            for k, v in dict(beta=beta, l1=l1, l2=l2, ortho=ortho, steps=3).items():
+                flat[f"{name}/{k}"] = np.array(v, dtype=np.float64)
+    # --- PLCA: small ragged case (Dirichlet priors, frozen Z) and a tensor-core-shaped case ---
+    for name, (N, C, R, iters, kw, fitkw) in {
+        "plca_small": (97, 83, 8, 30, {}, {}),
+        "plca_prior": (97, 83, 8, 30, {}, dict(W_alpha=1.05, H_alpha=1.02, Z_alpha=1.1)),
+        "plca_frozenZ": (97, 83, 8, 20, dict(trainable_Z=False), {}),
+        "plca_tc": (1024, 512, 32, 50, {}, {}),
+    }.items():
+        torch.manual_seed(0)
+        V = torch.rand(N, C).bfloat16().float() * 3
+        torch.manual_seed(1)
+        W0 = torch.randn(C, R).abs(); H0 = torch.randn(N, R).abs(); Z0 = torch.rand(R) + 0.1
+        m = ref_plca.PLCA(W=W0, H=H0, Z=Z0, **kw)
+        n_iter, norm = m.fit(V, float("-inf"), iters, False, **fitkw)
+        for k, v in dict(V=V, W0=W0, H0=H0, Z0=Z0, W=m.W.detach().clone(), H=m.H.detach().clone(),
+                         Z=m.Z.detach().clone()).items():
+            flat[f"{name}/{k}"] = v.numpy()
+        flat[f"{name}/n_iter"] = np.array(n_iter); flat[f"{name}/norm"] = np.array(float(norm)); flat[f"{name}/iters"] = np.array(iters)
+        flat[f"{name}/trainable_Z"] = np.array(int(kw.get("trainable_Z", True)))
+        for k in ("W_alpha", "H_alpha", "Z_alpha"):
+            flat[f"{name}/{k}"] = np.array(float(fitkw.get(k, 1.0)))
+    np.savez_compressed(os.path.join(GOLD, "reference_next.npz"), **flat)
+    print(f"wrote reference_next.npz ({os.path.getsize(os.path.join(GOLD, 'reference_next.npz')) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg2", action="store_true")
     ap.add_argument("--only-cfg2", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--r2", action="store_true", help="only the round-2 fixtures (reference_r2.npz)")
+    ap.add_argument("--next-rows", action="store_true", help="only the BetaMu / PLCA fixtures (reference_next.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.next_rows:
+        next_row_cases()
+        sys.exit(0)
     if a.r2:
         round2_cases()
         sys.exit(0)

@@ -368,6 +368,34 @@ int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, doub
   return reduce_chunks(ctx->den, ctx->nch_w, CR, ctx->C, (int)ctx->R, ctx->R, partial + CR, st);
 }
 
+int64_t nmfb200_nmf_raw_terms_numel(const nmfb200_ctx* ctx, int which, double beta) {
+  if (!ctx || ctx->kind != 0 || (which != 0 && which != 1)) return -1;
+  const int64_t rows = which == 0 ? ctx->C : ctx->N;
+  return beta == 1.0 ? rows * ctx->R + ctx->R : 2 * rows * ctx->R;
+}
+
+int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta, float* out,
+                          void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !out || (which != 0 && which != 1)) return fail(NMFB200_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(ctx, beta) && tc_supports_partial(ctx->tc, beta)) return tc_raw_terms(ctx->tc, which, W, H, beta, out, st);
+  int rc = which == 0 ? simt_contract_w(ctx, W, H, beta, st) : simt_contract_h(ctx, W, H, beta, st);
+  if (rc) return rc;
+  const int64_t rows = which == 0 ? ctx->C : ctx->N;
+  const int64_t RR = rows * ctx->R;
+  const int nch = which == 0 ? ctx->nch_w : ctx->nch_h;
+  rc = reduce_chunks(ctx->num, nch, RR, rows, (int)ctx->R, ctx->R, out, st);
+  if (rc) return rc;
+  if (beta == 1.0) {      // nmf.py:122-131: the KL denominator is the column sum of the OTHER factor
+    const float* other = which == 0 ? H : W;
+    return factor_colsum(other, which == 0 ? ctx->N : ctx->C, (int)ctx->R, 1, ctx->cs_scratch, ctx->cs_scratch_floats,
+                         out + RR, st);
+  }
+  return reduce_chunks(ctx->den, nch, RR, rows, (int)ctx->R, ctx->R, out + RR, st);
+}
+
 int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced, double beta, double gamma,
                         double l1_reg, double l2_reg, void* stream) {
   CTX_GUARD(ctx, 0);

@@ -1999,20 +1999,27 @@ int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double
   return 0;
 }
 
-int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st) {
+// Raw update terms of one factor (which = 0: W, 1: H) in one dense buffer: numerator (rows x R; chunk sums, + kappa
+// colsum(other) for beta 1, since the kernel accumulated sum (P - kappa) G) followed by colsum(other factor) (R, beta 1) or
+// the raw denominator (rows x R).  One contraction launch + one pack launch.
+int tc_raw_terms(TcState* s, int which, const float* W, const float* H, double beta, float* out, cudaStream_t st) {
   int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, 0, beta, st);
+  rc = launch_contract(s, which, beta, st);
   if (rc) return rc;
-  // one launch packs the all-reduce buffer: numerator (chunk sums, + kappa colsum(H_local) for beta 1, since the kernel
-  // accumulated sum_n (P - kappa) H) followed by colsum(H_local) (beta 1) or the raw denominator (include/nmf_b200.h)
-  const int64_t CR = s->C * s->R;
-  const int64_t total = beta == 1.0 ? CR + s->R : 2 * CR;
+  const int64_t rows = which == 0 ? s->C : s->N;
+  const Plan& pl = which == 0 ? s->plan_w : s->plan_h;
+  const int64_t RR = rows * s->R;
+  const int64_t total = beta == 1.0 ? RR + s->R : 2 * RR;
   w_partial_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
-      s->part, beta == 1.0 ? nullptr : s->part2, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp,
-      s->colsum + s->R, s->kappa, partial);
+      s->part, beta == 1.0 ? nullptr : s->part2, pl.nchunks, rows * s->Rp, rows, (int)s->R, s->Rp,
+      s->colsum + (1 - which) * s->R, s->kappa, out);
   NMF_LAUNCH_CHECK();
   return 0;
+}
+
+int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st) {
+  return tc_raw_terms(s, 0, W, H, beta, partial, st);
 }
 
 // Sharded W update, second half: nmf.py:78-92 on the all-reduced buffer with the tensor-core path's own ratio-stage

@@ -29,6 +29,8 @@ int tc_update_h(TcState* s, const float* W, float* H, double beta, double gamma,
 int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double l1, double l2, int n_iter,
                cudaStream_t st);
 int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float* partial, cudaStream_t st);
+// the same for either factor (which = 0: W, 1: H): [numerator rows x R | colsum(other) R (beta 1) or denominator rows x R]
+int tc_raw_terms(TcState* s, int which, const float* W, const float* H, double beta, float* out, cudaStream_t st);
 int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double gamma, double l1, double l2,
                cudaStream_t st);
 int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st);

@@ -38,6 +38,8 @@ SIGNATURES = {
     "nmfb200_nmf_loss": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
     "nmfb200_nmf_w_partial_numel": (_i64, [_vp, _dbl]),
     "nmfb200_nmf_w_partial": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
+    "nmfb200_nmf_raw_terms_numel": (_i64, [_vp, _int, _dbl]),
+    "nmfb200_nmf_raw_terms": (_int, [_vp, _vp, _vp, _int, _dbl, _vp, _vp]),
     "nmfb200_nmf_w_apply": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmf_contract_only": (_int, [_vp, _vp, _vp, _int, _dbl, _vp]),
     "nmfb200_nmfd_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _i64, _i64, _int]),

@@ -165,6 +165,19 @@ class CudaNmfEngine(_CudaEngine):
                                                     _stream(self.device)))
         return buf
 
+    def raw_terms(self, which, beta):
+        """(numerator, denominator) of the update of W (which=0) or H (which=1) from the CURRENT factors, untouched:
+        numerator (rows, R); denominator (R,) for beta == 1 (the column sums of the other factor) else (rows, R).
+        What BetaMu.step and PLCA.fit are built from (include/nmf_b200.h: nmfb200_nmf_raw_terms)."""
+        n = int(self._lib.nmfb200_nmf_raw_terms_numel(self._ctx, int(which), float(beta)))
+        buf = torch.empty(n, dtype=torch.float32, device=self.device)
+        _capi.check(self._lib.nmfb200_nmf_raw_terms(self._ctx, _ptr(self.W), _ptr(self.H), int(which), float(beta),
+                                                    _ptr(buf), _stream(self.device)))
+        rows = self.C if which == 0 else self.N
+        num = buf[:rows * self.R].view(rows, self.R)
+        den = buf[rows * self.R:]
+        return num, (den if beta == 1 else den.view(rows, self.R))
+
     def w_apply(self, reduced, beta, gamma, l1_reg, l2_reg):
         _capi.check(self._lib.nmfb200_nmf_w_apply(self._ctx, _ptr(self.W), _ptr(reduced), beta, gamma, l1_reg,
                                                   l2_reg, _stream(self.device)))

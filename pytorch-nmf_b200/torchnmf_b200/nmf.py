@@ -15,6 +15,7 @@ mode, the `e2e` number of bench.py).  Without a CUDA device or without the built
 Out of scope: sparse targets, `sparse_fit`, NMF2D/NMF3D, PLCA, trainers.
 """
 import math
+import weakref
 from collections.abc import Iterable as _Iterable
 
 import torch
@@ -99,11 +100,17 @@ class BaseComponent(torch.nn.Module):
 
     def forward(self, H=None, W=None):
         """Reconstruction only (nmf.py:261-284); plain differentiable torch ops, not on the fit path."""
+        own = H is None and W is None
         H = self.H if H is None else H
         W = self.W if W is None else W
         assert H is not None
         assert W is not None
-        return self.reconstruct(H, W)
+        out = self.reconstruct(H, W)
+        if own and type(self) is NMF:
+            # the plain reconstruction of this module's own factors: lets trainer.BetaMu recognise a single-leaf graph
+            # and take both update terms from the fused kernels instead of two backward passes through `out`
+            out._nmf_b200_src = weakref.ref(self)
+        return out
 
     @staticmethod
     def reconstruct(H, W):
