@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "tc_nmf.cuh"
+#include "tc_nmfd.cuh"
 
 namespace nmfb200 {
 static thread_local std::string g_err;
@@ -43,8 +44,9 @@ struct nmfb200_ctx {
   float* Pn = nullptr;
   float* Pp = nullptr;
   int dgrad_nsplit = 1;
-  // tensor-core path state (tc_nmf.cu)
+  // tensor-core path state (tc_nmf.cu / tc_nmfd.cu)
   TcState* tc = nullptr;
+  TcNmfdState* tcd = nullptr;
 };
 
 namespace {
@@ -93,6 +95,7 @@ void free_ctx(nmfb200_ctx* c) {
   if (!c) return;
   DeviceGuard guard(c->device);
   if (c->tc) tc_destroy(c->tc);
+  if (c->tcd) tc_nmfd_destroy(c->tcd);
   cudaFree(c->num); cudaFree(c->den); cudaFree(c->colsum); cudaFree(c->cs_scratch);
   cudaFree(c->loss_blocks); cudaFree(c->mm_scratch); cudaFree(c->Pn); cudaFree(c->Pp);
   delete c;
@@ -141,6 +144,7 @@ int nmfb200_ctx_check_health(nmfb200_ctx* ctx, void* stream) {
 
 int nmfb200_check_health(void* stream) {
   int rc = tc_check_wait_abort((cudaStream_t)stream);
+  if (rc == 0) rc = tc_nmfd_check_wait_abort();
   if (rc > 0) return fail(NMFB200_ERR_STATE, "a kernel aborted an internal barrier wait; results are invalid");
   if (rc < 0) return fail(NMFB200_ERR_CUDA, std::string("stream synchronize: ") + cudaGetErrorString(cudaGetLastError()));
   return 0;
@@ -203,6 +207,7 @@ int nmfb200_precision(const nmfb200_ctx* ctx) {
 
 int nmfb200_precision_for_beta(const nmfb200_ctx* ctx, double beta) {
   if (!ctx) return -100;
+  if (ctx->kind == 1) return (ctx->tcd && !ctx->tc_off && tc_nmfd_supported(ctx->d, beta)) ? NMFB200_PREC_F16 : NMFB200_PREC_F32;
   if (ctx->kind != 0 || !use_tc(ctx, beta)) return NMFB200_PREC_F32;
   // beta != 1 kernels read only the hi halves of the operand copies
   return (beta == 1.0 || beta == 2.0) ? ctx->precision : NMFB200_PREC_F16;
@@ -432,14 +437,15 @@ int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int
   *out = nullptr;
   if (B < 1 || C < 1 || R < 1 || T < 1 || L < T) return fail(NMFB200_ERR_INVALID, "bad NMFD sizes");
   if (R > 256) return fail(NMFB200_ERR_INVALID, "rank > 256 is not supported");
-  if (precision != NMFB200_PREC_AUTO && precision != NMFB200_PREC_F32)
-    return fail(NMFB200_ERR_INVALID, "NMFD currently runs in fp32 only");
+  if (precision != NMFB200_PREC_AUTO && precision != NMFB200_PREC_F32 && precision != NMFB200_PREC_F16)
+    return fail(NMFB200_ERR_INVALID, "NMFD precision must be auto, f32 or f16");
   if (B * C * L > (int64_t)1 << 40) return fail(NMFB200_ERR_INVALID, "NMFD target too large");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(NMFB200_ERR_CUDA, "cannot select the requested device");
   nmfb200_ctx* c = new (std::nothrow) nmfb200_ctx();
   if (!c) return fail(NMFB200_ERR_INVALID, "out of host memory");
-  c->kind = 1; c->device = device; c->precision = NMFB200_PREC_F32; c->R = R;
+  c->kind = 1; c->device = device; c->precision = precision == NMFB200_PREC_F32 ? NMFB200_PREC_F32 : NMFB200_PREC_F16; c->R = R;
+  c->auto_mode = precision == NMFB200_PREC_AUTO;
   c->d = NmfdShape{(int)B, (int)C, (int)L, (int)R, (int)T, (int)(L - T + 1)};
   c->dgrad_nsplit = nmfd_dgrad_nsplit(c->d);
   int64_t pf = C * R * T;
@@ -460,6 +466,16 @@ int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int
     free_ctx(c);
     return fail(NMFB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   }
+  if (c->precision != NMFB200_PREC_F32) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.major == 10) {
+      int rc = tc_nmfd_create(&c->tcd, c->d);          // beta = 1 runs as tcgen05 sliding GEMMs (tc_nmfd.cu)
+      if (rc) { free_ctx(c); return rc; }
+    } else if (precision == NMFB200_PREC_F16) {
+      free_ctx(c);
+      return fail(NMFB200_ERR_INVALID, "the tensor-core NMFD path needs an sm_100 device");
+    }
+  }
   *out = c;
   return 0;
 }
@@ -468,8 +484,36 @@ int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream) {
   CTX_GUARD(ctx, 1);
   if (!V) return fail(NMFB200_ERR_INVALID, "null target");
   ctx->V = V; ctx->has_target = true;
-  return matrix_minmax(V, (int64_t)ctx->d.B * ctx->d.C, ctx->d.L, ctx->d.L, ctx->mm_scratch,
-                       ctx->mm_scratch + 2048, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = matrix_minmax(V, (int64_t)ctx->d.B * ctx->d.C, ctx->d.L, ctx->d.L, ctx->mm_scratch, ctx->mm_scratch + 2048, st);
+  if (rc) return rc;
+  ctx->tc_off = false;
+  if (ctx->tcd) {
+    double vsum = 0.0;
+    rc = tc_nmfd_set_target(ctx->tcd, V, &vsum, st);       // synchronises: sum(V) for kappa
+    if (rc) return rc;
+    if (ctx->auto_mode) {                                 // same conservative rule as the NMF path: heavy-tailed targets stay fp32
+      float mm[2] = {0.f, 0.f};
+      NMF_CUDA_CHECK(cudaMemcpyAsync(mm, ctx->mm_scratch + 2048, sizeof(mm), cudaMemcpyDeviceToHost, st));
+      NMF_CUDA_CHECK(cudaStreamSynchronize(st));
+      const double mean = vsum / ((double)ctx->d.B * ctx->d.C * ctx->d.L);
+      ctx->tc_off = !(mean > 0.0) || (double)mm[1] > 64.0 * mean;
+    }
+  }
+  return 0;
+}
+
+// beta = 1 on tensor cores: both column-sum vectors (KL denominators, nmf.py:122-131, and kappa), then the recon pass
+static bool nmfd_use_tc(const nmfb200_ctx* c, double beta) {
+  return c->tcd != nullptr && !c->tc_off && tc_nmfd_supported(c->d, beta);
+}
+static int nmfd_tc_recon(nmfb200_ctx* c, const float* W, const float* H, bool loss, double* loss_dev, cudaStream_t st) {
+  const NmfdShape& d = c->d;
+  int rc = factor_colsum(W, d.C, d.R, d.T, c->cs_scratch, c->cs_scratch_floats, c->colsum, st);
+  if (rc) return rc;
+  rc = factor_colsum(H, d.B, d.R, d.Lin, c->cs_scratch, c->cs_scratch_floats, c->colsum + d.R, st);
+  if (rc) return rc;
+  return tc_nmfd_recon(c->tcd, c->V, W, H, c->colsum, loss, loss_dev, st);
 }
 
 static int nmfd_phi(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
@@ -488,6 +532,19 @@ int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double bet
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const NmfdShape& d = ctx->d;
+  if (nmfd_use_tc(ctx, beta)) {
+    int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
+    if (rc) return rc;
+    const float* part; int nsplit;
+    rc = tc_nmfd_wgrad(ctx->tcd, &part, &nsplit, st);
+    if (rc) return rc;
+    ApplyArgs a{};
+    a.param = W; a.numel = (int64_t)d.C * d.R * d.T; a.R = d.R; a.inner = d.T; a.rowlen = (int64_t)d.R * d.T;
+    a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
+    a.kl_den = ctx->colsum + d.R; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = ctx->colsum + d.R;
+    a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
+    return apply_update(a, st);
+  }
   int rc = nmfd_phi(ctx, W, H, beta, st);
   if (rc) return rc;
   rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, st);
@@ -515,6 +572,19 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double bet
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const NmfdShape& d = ctx->d;
+  if (nmfd_use_tc(ctx, beta)) {
+    int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
+    if (rc) return rc;
+    const float* part; int nsplit;
+    rc = tc_nmfd_dgrad(ctx->tcd, &part, &nsplit, st);
+    if (rc) return rc;
+    ApplyArgs a{};
+    a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;
+    a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
+    a.kl_den = ctx->colsum; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = ctx->colsum;
+    a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
+    return apply_update(a, st);
+  }
   int rc = nmfd_phi(ctx, W, H, beta, st);
   if (rc) return rc;
   rc = nmfd_dgrad(d, ctx->Pn, W, ctx->num, ctx->dgrad_nsplit, st);
@@ -540,6 +610,7 @@ int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double b
   CTX_GUARD(ctx, 1);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H || !loss_dev) return fail(NMFB200_ERR_INVALID, "null pointer");
+  if (nmfd_use_tc(ctx, beta)) return nmfd_tc_recon(ctx, W, H, true, loss_dev, (cudaStream_t)stream);
   return nmfd_recon_phi(ctx->d, ctx->V, W, H, beta, nullptr, nullptr, ctx->loss_blocks, ctx->loss_max_blocks,
                         loss_dev, (cudaStream_t)stream);
 }

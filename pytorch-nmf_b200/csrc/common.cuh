@@ -76,6 +76,8 @@ struct ApplyArgs {
   const float* out_scale;  // device scalar multiplying num/den partials (nullptr = 1)
   float gamma, l1, l2;
   unsigned int* absmax_bits;  // optional: atomicMax of the updated values (non-negative floats)
+  const float* kappa;         // optional (with kappa_vec): the partials hold sum (P - kappa) G; num += *kappa * kappa_vec[r]
+  const float* kappa_vec;     // [R]
 };
 int apply_update(const ApplyArgs& a, cudaStream_t st);
 // sums[r] = sum over all other dims of x viewed as (outer, R, inner); deterministic two-stage.

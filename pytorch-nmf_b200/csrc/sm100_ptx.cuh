@@ -67,18 +67,18 @@ __device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t pari
   return ok != 0;
 }
 #ifdef NMFB200_TRACE
-__device__ unsigned int g_tune_park;      // tuning build: non-zero = parked polls in mbar_wait_slow
+static __device__ unsigned int g_tune_park;      // tuning build: non-zero = parked polls in mbar_wait_slow
 #endif
 // Bounded wait: on a protocol bug (no progress for ~1 s) the first waiter records (block, thread, barrier, parity)
 // in g_wait_abort and every wait in the grid then falls through, so the kernel terminates instead of hanging
 // the GPU box; the host checks the record after the launch (tc_nmf.cu: check_wait_abort).
-__device__ unsigned int g_wait_abort[8];
+static __device__ unsigned int g_wait_abort[8];      // one record per translation unit (tc_nmf.cu, tc_nmfd.cu)
 // Slow path of mbar_wait, out of line on purpose: the warp-specialised loops are latency-bound serial instruction
 // streams (one MMA-issuing warp feeds the whole SM), so every wait site inlines only try_wait + a predicated call.
 // The poll loop touches nothing but the barrier; the watchdog (clock, abort flag in global memory) is looked at once
 // per 1024 failed polls -- a global load per poll costs an L2 round trip under a saturated memory system and shows up
 // as microseconds of wake-up latency at every hand-off.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;
 #ifdef NMFB200_TRACE

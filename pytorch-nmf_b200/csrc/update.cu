@@ -18,6 +18,7 @@ apply_update_kernel(ApplyArgs a) {
     float num = 0.f;
     for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + off];
     num *= sc;
+    if (a.kappa) num = fmaf(*a.kappa, a.kappa_vec[r], num);
     const float p = a.param[idx];
     float neg = fmaxf(num, 0.f) + kEps;                      // nmf.py:78
     float pos;

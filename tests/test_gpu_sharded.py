@@ -44,7 +44,7 @@ def _worker(rank, world, port, precision, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("precision", ["f32", "f16_split"])
+@pytest.mark.parametrize("precision", ["f32", "f16_split", "auto"])
 def test_two_gpu_sharded_fit_matches_single(tmp_path, precision):
     from torchnmf_b200 import NMF
     mp.spawn(_worker, args=(2, _free_port(), precision, str(tmp_path)), nprocs=2, join=True)
@@ -55,6 +55,6 @@ def test_two_gpu_sharded_fit_matches_single(tmp_path, precision):
     assert parts[0]["n"] == parts[1]["n"] == n_ref
     assert torch.equal(parts[0]["W"], parts[1]["W"])                     # replicas stay bit-identical
     H = torch.cat([p["H"] for p in parts])
-    rtol = 1e-4 if precision == "f32" else 5e-4
+    rtol = 1e-4 if precision == "f32" else 1e-3      # fp16 operands: the north-star tolerance
     assert torch.allclose(parts[0]["W"], ref.W.data.cpu(), rtol=rtol, atol=1e-6)
     assert torch.allclose(H, ref.H.data.cpu(), rtol=rtol, atol=1e-6)
