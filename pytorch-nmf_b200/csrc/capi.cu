@@ -576,7 +576,7 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double bet
     int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
     if (rc) return rc;
     const float* part; int nsplit;
-    rc = tc_nmfd_dgrad(ctx->tcd, &part, &nsplit, st);
+    rc = tc_nmfd_dgrad(ctx->tcd, W, &part, &nsplit, st);
     if (rc) return rc;
     ApplyArgs a{};
     a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;

@@ -22,6 +22,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "sm100_ptx.cuh"
@@ -311,6 +312,155 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
   if (warp == 1) ptx::tmem_dealloc(tmem, ncols);
 }
 
+// ---- dgrad, second formulation: no Toeplitz tile is built at all ---------------------------------------------------------
+//   gH[r, 8q + s] = sum_c sum_u  P[c, 8q + u] * Ws[c, (r, s), u],      Ws[c, (r, s), u] = W[c, r, u - s]  (0 <= u - s < T)
+// With the output position split as j = 8q + s, the eight phases s move into the SMALL operand (eight shifted copies of W,
+// prepared once per update: N = (r, s) = 128 columns for 16 components), and the rows q of the big operand become windows
+// of P that start 8 elements = 16 BYTES apart: exactly the row pitch of a SWIZZLE_NONE K-major core matrix.  The A operand
+// of tcgen05.mma is therefore the raw fp16 row of P in shared memory, addressed by a descriptor whose core matrices overlap
+// (leading byte offset 16, stride byte offset 128): one 2.4 KB bulk copy per (c, 1024 output positions) instead of a
+// 128 x 64 tile per 64 shifts, and every MMA is a full-rate 128 x 128 x 16.  B = Ws tiles by TMA (SWIZZLE_128B).
+// grid (ceil(Lin / 2048), nsplit over c, B * ngroups);  2 accumulators (2 x 1024 output positions) share every B tile.
+constexpr int kD2Threads = 256;     // warp 0 TMA | warp 1 MMA | warps 4-7 epilogue
+constexpr int kD2Stages = 3;
+constexpr int kD2Q = 2;             // q tiles (accumulators) per CTA
+
+struct Dgrad2Params {
+  int B, C, R, Lin, Lq, Tq, ngroups;
+  const __half* P16;
+  const int* exps;
+  float* out;                       // [nsplit][B][R][Lin]
+  int c_per_split;
+};
+
+__global__ void __launch_bounds__(kD2Threads, 1)
+tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw32 = ptx::smem_u32(smem_raw);
+  const uint32_t sbase = (raw32 + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (sbase - raw32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkk = p.Tq / kKB;                                   // B tiles (64 columns of u each) per c
+  const uint32_t seg_bytes = (uint32_t)(1024 + p.Tq) * 2;       // P[c][8 q0 .. 8 q0 + 1024 + Tq)
+  const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;
+  const uint32_t stage_bytes = (uint32_t)nkk * Smem::kTile + kD2Q * seg_pitch;
+  const uint32_t bar0 = sbase + kD2Stages * ((stage_bytes + 1023u) & ~1023u);
+  auto STAGE = [&](int s) { return sbase + (uint32_t)s * ((stage_bytes + 1023u) & ~1023u); };
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int B_FULL = 0, B_EMPTY = kD2Stages, B_ACC = 2 * kD2Stages;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + (bar0 - sbase) + 8 * (2 * kD2Stages + 1));
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmWs);
+    for (int i = 0; i < kD2Stages; ++i) { ptx::mbar_init(BAR(B_FULL + i), 1); ptx::mbar_init(BAR(B_EMPTY + i), 1); }
+    ptx::mbar_init(BAR(B_ACC), 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(bar0 + 8 * (2 * kD2Stages + 1), 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const int b = blockIdx.z / p.ngroups, grp = blockIdx.z - b * p.ngroups;
+  const int c0 = blockIdx.y * p.c_per_split, c1 = min(p.C, c0 + p.c_per_split);
+  const int nc = max(0, c1 - c0);
+  const int j0 = blockIdx.x * (kD2Q * 1024);                    // first output position of this CTA
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nc; ++i) {
+        const int s = i % kD2Stages, ph = (i / kD2Stages) & 1, c = c0 + i;
+        ptx::mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+        ptx::mbar_expect_tx(BAR(B_FULL + s), (uint32_t)nkk * Smem::kTile + kD2Q * seg_bytes);
+        for (int kk = 0; kk < nkk; ++kk)
+          ptx::tma_load_2d(&tmWs, BAR(B_FULL + s), STAGE(s) + kk * Smem::kTile, kk * kKB, (c * p.ngroups + grp) * 128);
+        for (int qt = 0; qt < kD2Q; ++qt)
+          bulk_copy_g2s(STAGE(s) + nkk * Smem::kTile + qt * seg_pitch,
+                        p.P16 + ((int64_t)b * p.C + c) * p.Lq + j0 + qt * 1024, seg_bytes, BAR(B_FULL + s));
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::idesc_f16(kM, 128, 0, 0);
+    constexpr uint32_t descHiB = ptx::smem_desc_hi_sw128(1024);
+    constexpr uint32_t descHiA = ((128u >> 4) & 0x3FFFu) | (1u << 14);      // SWIZZLE_NONE, stride byte offset 128 (8 rows x 16 B)
+    for (int i = 0; i < nc; ++i) {
+      const int s = i % kD2Stages, ph = (i / kD2Stages) & 1;
+      if (lane == 0) ptx::mbar_wait(BAR(B_FULL + s), ph);
+      __syncwarp();
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        for (int qt = 0; qt < kD2Q; ++qt) {
+          const uint32_t seg = STAGE(s) + nkk * Smem::kTile + qt * seg_pitch;
+          for (int kk = 0; kk < nkk; ++kk) {
+#pragma unroll
+            for (int ks = 0; ks < kKB / 16; ++ks) {
+              // A: rows q = windows of the raw P row, 16 bytes apart; k-step = 16 elements = two core matrices 16 bytes apart
+              const uint32_t alo = ptx::smem_desc_lo(seg + (uint32_t)(kk * kKB + ks * 16) * 2, 16);
+              const uint32_t blo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
+              ptx::mma_ss(tmem + qt * 128, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc,
+                          (i | kk | ks) ? 1u : 0u);
+            }
+          }
+        }
+        ptx::mma_commit(BAR(B_EMPTY + s));
+        if (i == nc - 1) ptx::mma_commit(BAR(B_ACC));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, r128 = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    if (nc > 0) {
+      ptx::mbar_wait(BAR(B_ACC), 0);
+      ptx::tc_fence_after();
+    }
+    const float sc = exp2f(-(float)(p.exps[0] + p.exps[2]));
+    for (int qt = 0; qt < kD2Q; ++qt) {
+      const int j = j0 + qt * 1024 + 8 * r128;                   // this lane's 8 output positions
+#pragma unroll 1
+      for (int jj = 0; jj < 8; ++jj) {                            // 16 columns = 2 components x 8 phases
+        uint32_t sr[16];
+        if (nc > 0) { ptx::tmem_ld16(tmem + lane_addr + qt * 128 + jj * 16, sr); ptx::tc_wait_ld(); }
+        else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sr[i] = 0u;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = grp * 16 + jj * 2 + h;
+          if (r < p.R) {
+            float* dst = p.out + (((int64_t)blockIdx.y * p.B + b) * p.R + r) * p.Lin + j;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (j + i < p.Lin) dst[i] = __uint_as_float(sr[8 * h + i]) * sc;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 256);
+}
+
+// W (C, R, T) fp32 -> Ws16 [(c, group, (r % 16, s))][Tq]: Ws[c][(r, s)][u] = W[c, r, u - s] 2^eW, zero outside 0 <= u - s < T
+__global__ void __launch_bounds__(256)
+prep_ws_kernel(const float* __restrict__ W, int C, int R, int T, int Tq, int ngroups, const int* __restrict__ exps,
+               __half* __restrict__ Ws16) {
+  const float sc = exp2f((float)exps[0]);
+  const int c = blockIdx.x;
+  const int64_t rows = (int64_t)ngroups * 128;
+  for (int i = threadIdx.x; i < rows * Tq; i += 256) {
+    const int n = i / Tq, u = i - n * Tq;
+    const int r = (n >> 7) * 16 + ((n & 127) >> 3), s = n & 7, t = u - s;
+    const float w = (r < R && t >= 0 && t < T) ? W[((int64_t)c * R + r) * T + t] * sc : 0.f;
+    Ws16[((int64_t)c * rows + n) * Tq + u] = __float2half_rn(w);
+  }
+}
+
 // ---- operand preparation --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int pow2_exp14(float mx) {
   if (!(mx > 0.f) || !isfinite(mx)) return 0;
@@ -416,7 +566,8 @@ int make_tmap2(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int
 struct TcNmfdState {
   NmfdShape d{};
   int Tp = 0, Lp = 0, padl = 0, Lq = 0, Cpad = 0;
-  __half *Wr16 = nullptr, *Wf16 = nullptr, *Hp16 = nullptr, *P16 = nullptr;
+  __half *Wr16 = nullptr, *Wf16 = nullptr, *Hp16 = nullptr, *P16 = nullptr, *Ws16 = nullptr;
+  int Tq = 0, ngroups = 1, cps_h2 = 0, ws_h2 = 1;   // dgrad2: padded shift extent, 16-component groups, c per split, splits
   float* part = nullptr;            // wgrad / dgrad split partials
   int64_t part_floats = 0;
   unsigned int* absmax = nullptr;   // [2]
@@ -427,7 +578,7 @@ struct TcNmfdState {
   int loss_blocks = 0;
   int ws_w = 1, ws_h = 1;           // split counts of wgrad / dgrad
   int kbs_w = 0, kbs_h = 0;
-  CUtensorMap tmWr, tmWf, tmP;
+  CUtensorMap tmWr, tmWf, tmP, tmWs;
   bool attr_set = false;
 };
 
@@ -437,7 +588,7 @@ bool tc_nmfd_supported(const NmfdShape& d, double beta) {
 
 void tc_nmfd_destroy(TcNmfdState* s) {
   if (!s) return;
-  cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax);
+  cudaFree(s->Ws16); cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax);
   cudaFree(s->exps); cudaFree(s->kappa); cudaFree(s->vsum); cudaFree(s->loss_part);
   delete s;
 }
@@ -449,7 +600,9 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   s->Tp = (int)round_up(d.T, kKB);
   s->padl = (int)round_up(s->Tp + 136, 8);                       // every window start >= 0
   s->Lp = (int)round_up((int64_t)s->padl + d.L + kWinHalfs + 136, 8);
-  s->Lq = (int)round_up((int64_t)d.L + kWinHalfs + 8, 8);
+  s->Tq = (int)round_up(d.T + 7, kKB);
+  s->ngroups = (int)ceil_div(d.R, 16);
+  s->Lq = (int)round_up(round_up((int64_t)d.L, 2048) + 1024 + s->Tq + kWinHalfs + 8, 8);
   s->Cpad = (int)round_up(d.C, kM);
   const int lkb = (int)ceil_div(d.L, kKB), tkb = s->Tp / kKB;
   // split the K loops of wgrad / dgrad so that the grid is a few waves of 148 CTAs
@@ -459,7 +612,14 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   s->ws_h = (int)std::max<int64_t>(1, std::min<int64_t>(kb_h / 8, ceil_div(148 * 4, tiles_h)));
   s->kbs_w = (int)ceil_div(kb_w, s->ws_w); s->ws_w = (int)ceil_div(kb_w, s->kbs_w);
   s->kbs_h = (int)ceil_div(kb_h, s->ws_h); s->ws_h = (int)ceil_div(kb_h, s->kbs_h);
-  const int64_t pw = (int64_t)s->ws_w * d.C * d.R * d.T, ph = (int64_t)s->ws_h * d.B * d.R * d.Lin;
+  {
+    const int64_t tiles = ceil_div(d.Lin, kD2Q * 1024) * d.B * s->ngroups;
+    int64_t ws = std::max<int64_t>(1, std::min<int64_t>(d.C / 4 > 0 ? d.C / 4 : 1, ceil_div(148, tiles)));
+    s->cps_h2 = (int)ceil_div(d.C, ws);
+    s->ws_h2 = (int)ceil_div(d.C, s->cps_h2);
+  }
+  const int hs = std::max(s->ws_h, s->ws_h2);
+  const int64_t pw = (int64_t)s->ws_w * d.C * d.R * d.T, ph = (int64_t)hs * d.B * d.R * d.Lin;
   s->part_floats = pw > ph ? pw : ph;
   s->loss_blocks = (int)(ceil_div(d.L, kM) * ceil_div(d.C, kM) * d.B);
   const size_t wbytes = (size_t)s->Cpad * d.R * s->Tp * 2, hbytes = (size_t)d.B * d.R * s->Lp * 2;
@@ -467,6 +627,9 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMalloc(&s->Wr16, wbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->Wf16, wbytes);
+  const size_t wsbytes = (size_t)s->Cpad * s->ngroups * 128 * s->Tq * 2;
+  if (e == cudaSuccess) e = cudaMalloc(&s->Ws16, wsbytes);
+  if (e == cudaSuccess) e = cudaMemset(s->Ws16, 0, wsbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->Hp16, hbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->P16, pbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->part, (size_t)s->part_floats * 4);
@@ -491,6 +654,7 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   const int Rp16 = (d.R + 15) & ~15;
   rc |= make_tmap2(&s->tmWf, s->Wf16, (int64_t)s->Cpad * d.R, s->Tp, s->Tp, Rp16);
   rc |= make_tmap2(&s->tmP, s->P16, (int64_t)d.B * d.C, s->Lq, s->Lq, kM);
+  rc |= make_tmap2(&s->tmWs, s->Ws16, (int64_t)s->Cpad * s->ngroups * 128, s->Tq, s->Tq, 128);
   if (rc) { tc_nmfd_destroy(s); return 2; }
   *out = s;
   return 0;
@@ -576,7 +740,31 @@ int tc_nmfd_wgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t 
   return rc;
 }
 
-int tc_nmfd_dgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t st) {
+int tc_nmfd_dgrad(TcNmfdState* s, const float* W, const float** part, int* nsplit, cudaStream_t st) {
+  static const bool v1 = getenv("NMFB200_NMFD_DGRAD1") != nullptr;      // A/B: the Toeplitz-tile formulation
+  if (!v1) {
+    const NmfdShape& d = s->d;
+    prep_ws_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tq, s->ngroups, s->exps, s->Ws16);
+    NMF_LAUNCH_CHECK();
+    Dgrad2Params q{};
+    q.B = d.B; q.C = d.C; q.R = d.R; q.Lin = d.Lin; q.Lq = s->Lq; q.Tq = s->Tq; q.ngroups = s->ngroups;
+    q.P16 = s->P16; q.exps = s->exps; q.out = s->part; q.c_per_split = s->cps_h2;
+    const int nkk = s->Tq / kKB;
+    const uint32_t seg_pitch = (((uint32_t)(1024 + s->Tq) * 2) + 127u) & ~127u;
+    const uint32_t stage = (((uint32_t)nkk * Smem::kTile + kD2Q * seg_pitch) + 1023u) & ~1023u;
+    const int smem = (int)(kD2Stages * stage + 8 * (2 * kD2Stages + 1) + 16 + 1024);
+    if (smem > 232448) { set_error("nmfd dgrad: shift extent too large for the shared-memory stages"); return 1; }
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+      NMF_CUDA_CHECK(cudaFuncSetAttribute(tcnmfd_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_smem = smem;
+    }
+    dim3 grid((unsigned)ceil_div(d.Lin, kD2Q * 1024), (unsigned)s->ws_h2, (unsigned)(d.B * s->ngroups));
+    tcnmfd_dgrad2_kernel<<<grid, kD2Threads, smem, st>>>(s->tmWs, q);
+    NMF_LAUNCH_CHECK();
+    *part = s->part; *nsplit = s->ws_h2;
+    return 0;
+  }
   NmfdTcParams p = base_params(s, nullptr);
   p.nsplit = s->ws_h; p.kb_per_split = s->kbs_h;
   dim3 grid((unsigned)ceil_div(s->d.Lin, kM), (unsigned)s->ws_h, (unsigned)s->d.B);

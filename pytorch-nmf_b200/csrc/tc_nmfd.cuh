@@ -19,7 +19,7 @@ int tc_nmfd_recon(TcNmfdState* s, const float* V, const float* W, const float* H
 // split-K partial numerators from the ratio tile of the last recon: W side [nsplit][C][R][T], H side [nsplit][B][R][Lin]
 // (without the kappa * colsum term, which the ratio stage adds: ApplyArgs::kappa / kappa_vec)
 int tc_nmfd_wgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t st);
-int tc_nmfd_dgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t st);
+int tc_nmfd_dgrad(TcNmfdState* s, const float* W, const float** part, int* nsplit, cudaStream_t st);
 const float* tc_nmfd_kappa(const TcNmfdState* s);
 // after a stream synchronise: 1 if an NMFD kernel aborted an internal barrier wait since the last check (record cleared)
 int tc_nmfd_check_wait_abort();
