@@ -492,6 +492,7 @@ int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream) {
     double vsum = 0.0;
     rc = tc_nmfd_set_target(ctx->tcd, V, &vsum, st);       // synchronises: sum(V) for kappa
     if (rc) return rc;
+    tc_nmfd_mark_dirty(ctx->tcd);                         // a new fit: the factors may be anything
     if (ctx->auto_mode) {                                 // same conservative rule as the NMF path: heavy-tailed targets stay fp32
       float mm[2] = {0.f, 0.f};
       NMF_CUDA_CHECK(cudaMemcpyAsync(mm, ctx->mm_scratch + 2048, sizeof(mm), cudaMemcpyDeviceToHost, st));
@@ -508,12 +509,7 @@ static bool nmfd_use_tc(const nmfb200_ctx* c, double beta) {
   return c->tcd != nullptr && !c->tc_off && tc_nmfd_supported(c->d, beta);
 }
 static int nmfd_tc_recon(nmfb200_ctx* c, const float* W, const float* H, bool loss, double* loss_dev, cudaStream_t st) {
-  const NmfdShape& d = c->d;
-  int rc = factor_colsum(W, d.C, d.R, d.T, c->cs_scratch, c->cs_scratch_floats, c->colsum, st);
-  if (rc) return rc;
-  rc = factor_colsum(H, d.B, d.R, d.Lin, c->cs_scratch, c->cs_scratch_floats, c->colsum + d.R, st);
-  if (rc) return rc;
-  return tc_nmfd_recon(c->tcd, c->V, W, H, c->colsum, loss, loss_dev, st);
+  return tc_nmfd_recon(c->tcd, c->V, W, H, loss, loss_dev, st);
 }
 
 static int nmfd_phi(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
@@ -541,10 +537,13 @@ int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double bet
     ApplyArgs a{};
     a.param = W; a.numel = (int64_t)d.C * d.R * d.T; a.R = d.R; a.inner = d.T; a.rowlen = (int64_t)d.R * d.T;
     a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
-    a.kl_den = ctx->colsum + d.R; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = ctx->colsum + d.R;
+    const float* cs = tc_nmfd_colsum(ctx->tcd);
+    a.kl_den = cs + d.R; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = cs + d.R;
     a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
+    a.absmax_bits = tc_nmfd_begin_update(ctx->tcd, 0, st);
     return apply_update(a, st);
   }
+  if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);            // this update bypasses the tensor-core state
   int rc = nmfd_phi(ctx, W, H, beta, st);
   if (rc) return rc;
   rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, st);
@@ -576,15 +575,18 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double bet
     int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
     if (rc) return rc;
     const float* part; int nsplit;
-    rc = tc_nmfd_dgrad(ctx->tcd, W, &part, &nsplit, st);
+    rc = tc_nmfd_dgrad(ctx->tcd, &part, &nsplit, st);
     if (rc) return rc;
     ApplyArgs a{};
     a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;
     a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
-    a.kl_den = ctx->colsum; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = ctx->colsum;
+    const float* cs = tc_nmfd_colsum(ctx->tcd);
+    a.kl_den = cs; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = cs;
     a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
+    a.absmax_bits = tc_nmfd_begin_update(ctx->tcd, 1, st);
     return apply_update(a, st);
   }
+  if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);
   int rc = nmfd_phi(ctx, W, H, beta, st);
   if (rc) return rc;
   rc = nmfd_dgrad(d, ctx->Pn, W, ctx->num, ctx->dgrad_nsplit, st);

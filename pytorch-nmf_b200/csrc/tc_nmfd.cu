@@ -446,21 +446,6 @@ tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Param
   if (warp == 1) ptx::tmem_dealloc(tmem, 256);
 }
 
-// W (C, R, T) fp32 -> Ws16 [(c, group, (r % 16, s))][Tq]: Ws[c][(r, s)][u] = W[c, r, u - s] 2^eW, zero outside 0 <= u - s < T
-__global__ void __launch_bounds__(256)
-prep_ws_kernel(const float* __restrict__ W, int C, int R, int T, int Tq, int ngroups, const int* __restrict__ exps,
-               __half* __restrict__ Ws16) {
-  const float sc = exp2f((float)exps[0]);
-  const int c = blockIdx.x;
-  const int64_t rows = (int64_t)ngroups * 128;
-  for (int i = threadIdx.x; i < rows * Tq; i += 256) {
-    const int n = i / Tq, u = i - n * Tq;
-    const int r = (n >> 7) * 16 + ((n & 127) >> 3), s = n & 7, t = u - s;
-    const float w = (r < R && t >= 0 && t < T) ? W[((int64_t)c * R + r) * T + t] * sc : 0.f;
-    Ws16[((int64_t)c * rows + n) * Tq + u] = __float2half_rn(w);
-  }
-}
-
 // ---- operand preparation --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int pow2_exp14(float mx) {
   if (!(mx > 0.f) || !isfinite(mx)) return 0;
@@ -477,36 +462,104 @@ absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
-// W (C, R, T) fp32 -> Wr16 / Wf16 (Cpad rows x R*Tp): reversed-shift copy for recon (column r Tp + Tp-1-t) and forward copy
-// for dgrad (column r Tp + t), both scaled by 2^eW; block (c): also emits per-(c) partial column sums for colsum_W
+// One pass over W (C, R, T), block c: every fp16 operand copy of this row, scaled by 2^eW (eW from the max of W), written
+// 16 bytes per thread and step, plus the row's per-component sums (-> colsum_W, nmf.py:128-131):
+//   Wr16[c][r Tp + tt]           = W[c, r, Tp - 1 - tt]        (recon: shifts reversed so that the H window ascends)
+//   Wf16[c][r Tp + tt]           = W[c, r, tt]                 (dgrad, Toeplitz-tile formulation)
+//   Ws16[(c, grp, r%16, s)][u]   = W[c, r, u - s]              (dgrad, eight shifted copies)
 __global__ void __launch_bounds__(256)
-prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, const unsigned int* __restrict__ absmax,
-              int* __restrict__ exps, __half* __restrict__ Wr16, __half* __restrict__ Wf16) {
+prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, int ngroups,
+              const unsigned int* __restrict__ absmax, int* __restrict__ exps, __half* __restrict__ Wr16,
+              __half* __restrict__ Wf16, __half* __restrict__ Ws16, float* __restrict__ cs_part) {
   const int e = pow2_exp14(__uint_as_float(*absmax));
   if (blockIdx.x == 0 && threadIdx.x == 0) exps[0] = e;
   const float sc = exp2f((float)e);
   const int c = blockIdx.x;
+  const float* Wc = W + (int64_t)c * R * T;
+  auto w_at = [&](int r, int t) { return (r < R && t >= 0 && t < T) ? Wc[r * T + t] * sc : 0.f; };
+  auto pack8 = [&](const float (&v)[8]) {
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    return *reinterpret_cast<const uint4*>(h);
+  };
   const int64_t rowlen = (int64_t)R * Tp;
-  for (int i = threadIdx.x; i < R * Tp; i += 256) {
-    const int r = i / Tp, tt = i - r * Tp;
-    const float wf = tt < T ? W[((int64_t)c * R + r) * T + tt] * sc : 0.f;
-    Wf16[c * rowlen + i] = __float2half_rn(wf);
-    const int t = Tp - 1 - tt;
-    const float wr = t < T ? W[((int64_t)c * R + r) * T + t] * sc : 0.f;
-    Wr16[c * rowlen + i] = __float2half_rn(wr);
+  for (int i8 = threadIdx.x; i8 < R * Tp / 8; i8 += 256) {
+    const int i = i8 * 8, r = i / Tp, tt = i - r * Tp;
+    float f[8], rv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f[k] = w_at(r, tt + k); rv[k] = w_at(r, Tp - 1 - tt - k); }
+    *reinterpret_cast<uint4*>(Wf16 + c * rowlen + i) = pack8(f);
+    *reinterpret_cast<uint4*>(Wr16 + c * rowlen + i) = pack8(rv);
+  }
+  const int64_t rows = (int64_t)ngroups * 128;
+  for (int i8 = threadIdx.x; i8 < rows * Tq / 8; i8 += 256) {
+    const int i = i8 * 8, n = i / Tq, u = i - n * Tq;
+    const int r = (n >> 7) * 16 + ((n & 127) >> 3), sh = n & 7;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = w_at(r, u + k - sh);
+    *reinterpret_cast<uint4*>(Ws16 + ((int64_t)c * rows + n) * Tq + u) = pack8(v);
+  }
+  // per-component sums of this row: warp w takes r = w, w + 8, ...; fixed order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += 8) {
+    float a = 0.f;
+    for (int t = lane; t < T; t += 32) a += Wc[r * T + t];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) cs_part[(int64_t)c * R + r] = a;
   }
 }
 
-// H (B, R, Lin) fp32 -> Hp16 (B*R rows x Lp): H[b,r,j] at column padl + j, zeros elsewhere (set once at allocation)
+// H (B, R, Lin) fp32 -> Hp16 (B R rows x Lp): H[b,r,j] 2^eH at column padl + j (margins stay zero), 2048 elements per
+// block, + the block's partial sum (-> colsum_H, nmf.py:122-125).  grid (chunks, B R)
 __global__ void __launch_bounds__(256)
-prep_h_kernel(const float* __restrict__ H, int64_t rows, int Lin, int Lp, int padl, const unsigned int* __restrict__ absmax,
-              int* __restrict__ exps, __half* __restrict__ Hp16) {
+prep_h_kernel(const float* __restrict__ H, int Lin, int Lp, int padl, const unsigned int* __restrict__ absmax,
+              int* __restrict__ exps, __half* __restrict__ Hp16, float* __restrict__ cs_part) {
+  __shared__ float sh[8];
   const int e = pow2_exp14(__uint_as_float(*absmax));
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) exps[1] = e;
   const float sc = exp2f((float)e);
   const int64_t row = blockIdx.y;
-  for (int j = blockIdx.x * 256 + threadIdx.x; j < Lin; j += gridDim.x * 256)
-    Hp16[row * Lp + padl + j] = __float2half_rn(H[row * Lin + j] * sc);
+  const int j = blockIdx.x * 2048 + threadIdx.x * 8;
+  float a = 0.f;
+  if (j < Lin) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = j + k < Lin ? H[row * Lin + j + k] : 0.f; a += v[k]; v[k] *= sc; }
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(Hp16 + row * Lp + padl + j) = *reinterpret_cast<const uint4*>(h);
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    cs_part[row * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// colsum[r] = sum over `outer` slabs of `inner` consecutive partials each: part[(o R + r) inner + i]; block r, fixed order
+__global__ void __launch_bounds__(256)
+fold_colsum_kernel(const float* __restrict__ part, int outer, int R, int inner, float* __restrict__ colsum) {
+  __shared__ float sh[256];
+  const int r = blockIdx.x;
+  const int64_t n = (int64_t)outer * inner;
+  float a = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const int64_t o = i / inner, k = i - o * inner;
+    a += part[(o * R + r) * inner + k];
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) colsum[r] = sh[0];
 }
 
 // kappa = sum(V) / sum_r colsum_W[r] colsum_H[r] (= sum of the reconstruction, nmf.py:776-779) and the exponent of the ratio
@@ -570,7 +623,11 @@ struct TcNmfdState {
   int Tq = 0, ngroups = 1, cps_h2 = 0, ws_h2 = 1;   // dgrad2: padded shift extent, 16-component groups, c per split, splits
   float* part = nullptr;            // wgrad / dgrad split partials
   int64_t part_floats = 0;
-  unsigned int* absmax = nullptr;   // [2]
+  unsigned int* absmax = nullptr;   // [2]: max of W, max of H (float bits; written by absmax_kernel or by the ratio stage)
+  float* colsum = nullptr;          // [2][R]: colsum_W | colsum_H
+  float* cs_part = nullptr;         // per-row / per-block partial sums of the factor being refreshed
+  bool w_fresh = false, h_fresh = false;      // the fp16 copies / column sums of W, H match the fp32 factor
+  bool aw_valid = false, ah_valid = false;    // absmax[0], absmax[1] hold the max of the current W, H
   int* exps = nullptr;              // {eW, eH, eP}
   float* kappa = nullptr;
   double* vsum = nullptr;           // [1] + [256] partials
@@ -588,7 +645,7 @@ bool tc_nmfd_supported(const NmfdShape& d, double beta) {
 
 void tc_nmfd_destroy(TcNmfdState* s) {
   if (!s) return;
-  cudaFree(s->Ws16); cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax);
+  cudaFree(s->Ws16); cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax); cudaFree(s->colsum); cudaFree(s->cs_part);
   cudaFree(s->exps); cudaFree(s->kappa); cudaFree(s->vsum); cudaFree(s->loss_part);
   delete s;
 }
@@ -634,6 +691,11 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   if (e == cudaSuccess) e = cudaMalloc(&s->P16, pbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->part, (size_t)s->part_floats * 4);
   if (e == cudaSuccess) e = cudaMalloc(&s->absmax, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&s->colsum, 2 * (size_t)d.R * sizeof(float));
+  {
+    const int64_t np = std::max<int64_t>((int64_t)d.C * d.R, (int64_t)d.B * d.R * ceil_div(d.Lin, 2048));
+    if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, (size_t)np * sizeof(float));
+  }
   if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->vsum, 257 * sizeof(double));
@@ -696,29 +758,51 @@ NmfdTcParams base_params(TcNmfdState* s, const float* V) {
   return p;
 }
 
-// refresh the fp16 operand copies of W and H, and kappa (colsum = [colsum_W | colsum_H], already computed by the caller)
-int refresh(TcNmfdState* s, const float* W, const float* H, const float* colsum, cudaStream_t st) {
+// bring the fp16 operand copies, column sums (and with them kappa) up to date with the fp32 factors: only what changed
+int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
   const NmfdShape& d = s->d;
-  NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax, 0, 2 * sizeof(unsigned int), st));
-  absmax_kernel<<<256, 256, 0, st>>>(W, (int64_t)d.C * d.R * d.T, s->absmax);
-  NMF_LAUNCH_CHECK();
-  absmax_kernel<<<256, 256, 0, st>>>(H, (int64_t)d.B * d.R * d.Lin, s->absmax + 1);
-  NMF_LAUNCH_CHECK();
-  prep_w_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->absmax, s->exps, s->Wr16, s->Wf16);
-  NMF_LAUNCH_CHECK();
-  dim3 gh((unsigned)std::min<int64_t>(ceil_div(d.Lin, 256), 64), (unsigned)(d.B * d.R));
-  prep_h_kernel<<<gh, 256, 0, st>>>(H, (int64_t)d.B * d.R, d.Lin, s->Lp, s->padl, s->absmax + 1, s->exps, s->Hp16);
-  NMF_LAUNCH_CHECK();
-  kappa_kernel<<<1, 32, 0, st>>>(s->vsum, colsum, d.R, s->kappa, s->exps);
-  NMF_LAUNCH_CHECK();
+  const bool any = !s->w_fresh || !s->h_fresh;
+  if (!s->w_fresh) {
+    if (!s->aw_valid) {
+      NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax, 0, sizeof(unsigned int), st));
+      absmax_kernel<<<256, 256, 0, st>>>(W, (int64_t)d.C * d.R * d.T, s->absmax);
+      NMF_LAUNCH_CHECK();
+      s->aw_valid = true;
+    }
+    prep_w_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->Tq, s->ngroups, s->absmax, s->exps, s->Wr16, s->Wf16,
+                                       s->Ws16, s->cs_part);
+    NMF_LAUNCH_CHECK();
+    fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.C, d.R, 1, s->colsum);
+    NMF_LAUNCH_CHECK();
+    s->w_fresh = true;
+  }
+  if (!s->h_fresh) {
+    if (!s->ah_valid) {
+      NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax + 1, 0, sizeof(unsigned int), st));
+      absmax_kernel<<<256, 256, 0, st>>>(H, (int64_t)d.B * d.R * d.Lin, s->absmax + 1);
+      NMF_LAUNCH_CHECK();
+      s->ah_valid = true;
+    }
+    const int nch = (int)ceil_div(d.Lin, 2048);
+    dim3 gh((unsigned)nch, (unsigned)(d.B * d.R));
+    prep_h_kernel<<<gh, 256, 0, st>>>(H, d.Lin, s->Lp, s->padl, s->absmax + 1, s->exps, s->Hp16, s->cs_part);
+    NMF_LAUNCH_CHECK();
+    fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.B, d.R, nch, s->colsum + d.R);
+    NMF_LAUNCH_CHECK();
+    s->h_fresh = true;
+  }
+  if (any) {
+    kappa_kernel<<<1, 32, 0, st>>>(s->vsum, s->colsum, d.R, s->kappa, s->exps);
+    NMF_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 }  // namespace
 
-int tc_nmfd_recon(TcNmfdState* s, const float* V, const float* W, const float* H, const float* colsum, bool loss,
-                  double* loss_dev, cudaStream_t st) {
-  int rc = refresh(s, W, H, colsum, st);
+int tc_nmfd_recon(TcNmfdState* s, const float* V, const float* W, const float* H, bool loss, double* loss_dev,
+                  cudaStream_t st) {
+  int rc = refresh(s, W, H, st);
   if (rc) return rc;
   NmfdTcParams p = base_params(s, V);
   dim3 grid((unsigned)ceil_div(s->d.L, kM), (unsigned)ceil_div(s->d.C, kM), (unsigned)s->d.B);
@@ -740,12 +824,10 @@ int tc_nmfd_wgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t 
   return rc;
 }
 
-int tc_nmfd_dgrad(TcNmfdState* s, const float* W, const float** part, int* nsplit, cudaStream_t st) {
+int tc_nmfd_dgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t st) {
   static const bool v1 = getenv("NMFB200_NMFD_DGRAD1") != nullptr;      // A/B: the Toeplitz-tile formulation
   if (!v1) {
     const NmfdShape& d = s->d;
-    prep_ws_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tq, s->ngroups, s->exps, s->Ws16);
-    NMF_LAUNCH_CHECK();
     Dgrad2Params q{};
     q.B = d.B; q.C = d.C; q.R = d.R; q.Lin = d.Lin; q.Lq = s->Lq; q.Tq = s->Tq; q.ngroups = s->ngroups;
     q.P16 = s->P16; q.exps = s->exps; q.out = s->part; q.c_per_split = s->cps_h2;
@@ -774,6 +856,22 @@ int tc_nmfd_dgrad(TcNmfdState* s, const float* W, const float** part, int* nspli
 }
 
 const float* tc_nmfd_kappa(const TcNmfdState* s) { return s->kappa; }
+const float* tc_nmfd_colsum(const TcNmfdState* s) { return s->colsum; }
+
+// The caller is about to overwrite a factor (which = 0: W, 1: H) with its ratio stage: returns the slot the stage should
+// atomicMax the new values into (zeroed here), so the next refresh needs no separate pass for the operand exponent.
+unsigned int* tc_nmfd_begin_update(TcNmfdState* s, int which, cudaStream_t st) {
+  unsigned int* slot = s->absmax + which;
+  if (cudaMemsetAsync(slot, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
+  if (which == 0) { s->w_fresh = false; s->aw_valid = true; } else { s->h_fresh = false; s->ah_valid = true; }
+  return slot;
+}
+
+// a factor was changed by someone else: everything derived from it is stale
+void tc_nmfd_mark_dirty(TcNmfdState* s) {
+  s->w_fresh = s->h_fresh = false;
+  s->aw_valid = s->ah_valid = false;
+}
 
 // report (and clear) a recorded mbarrier wait abort of the NMFD kernels; the caller has synchronised the stream
 int tc_nmfd_check_wait_abort() {
