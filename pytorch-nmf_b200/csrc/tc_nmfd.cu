@@ -322,7 +322,7 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
 // 128 x 64 tile per 64 shifts, and every MMA is a full-rate 128 x 128 x 16.  B = Ws tiles by TMA (SWIZZLE_128B).
 // grid (ceil(Lin / 2048), nsplit over c, B * ngroups);  2 accumulators (2 x 1024 output positions) share every B tile.
 constexpr int kD2Threads = 256;     // warp 0 TMA | warp 1 MMA | warps 4-7 epilogue
-constexpr int kD2Stages = 3;
+constexpr int kD2Stages = 2;     // per CTA; two CTAs per SM (one in its epilogue while the other runs its main loop)
 constexpr int kD2Q = 2;             // q tiles (accumulators) per CTA
 
 struct Dgrad2Params {
@@ -333,7 +333,7 @@ struct Dgrad2Params {
   int c_per_split;
 };
 
-__global__ void __launch_bounds__(kD2Threads, 1)
+__global__ void __launch_bounds__(kD2Threads, 2)
 tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw32 = ptx::smem_u32(smem_raw);
@@ -446,6 +446,155 @@ tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Param
   if (warp == 1) ptx::tmem_dealloc(tmem, 256);
 }
 
+// ---- recon, second formulation: the same eight-phase trick on the H side ---------------------------------------------------
+//   S[c, 8q + s] = sum_r sum_u  Wsh[(c, s), (r, u)] * H[r, 8q + u - A],      Wsh[(c, s), (r, u)] = W[c, r, s + A - u]
+// (A = T - 1 rounded up to 8, so that the window of H that row q reads starts 16-byte aligned).  M = 16 rows c x 8 phases s
+// from eight shifted copies of W (TMA, SWIZZLE_128B), N = 256 positions q = the raw padded fp16 row of H in shared memory
+// through an overlapping SWIZZLE_NONE descriptor (rows 16 bytes apart): no Toeplitz tile, every MMA a 128 x 256 x 16.
+// Epilogue: TMEM lane (c, s), column q  <->  S[c, 8q + s]; the eight phases of a row are neighbouring lanes, so the fp32
+// reads of V and the fp16 writes of the ratio tile coalesce across lanes.
+// grid (ceil(L / 2048), ceil(C / 16), B)
+constexpr int kR2N = 256;
+
+struct Recon2Params {
+  int B, C, L, R, Lp, padl, Lq, Tq, A8;
+  const __half* Hp16;
+  __half* P16out;
+  const float* V;
+  const int* exps;
+  const float* kappa;
+  double* loss_part;
+};
+
+template <bool LOSS>
+__global__ void __launch_bounds__(kD2Threads, 2)
+tcnmfd_recon2_kernel(const __grid_constant__ CUtensorMap tmWsh, const Recon2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw32 = ptx::smem_u32(smem_raw);
+  const uint32_t sbase = (raw32 + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (sbase - raw32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkk = p.Tq / kKB;
+  const uint32_t seg_bytes = (uint32_t)(8 * kR2N + p.Tq) * 2;
+  const uint32_t stage_pitch = ((uint32_t)nkk * Smem::kTile + seg_bytes + 1023u) & ~1023u;
+  const uint32_t bar0 = sbase + kD2Stages * stage_pitch;
+  auto STAGE = [&](int s) { return sbase + (uint32_t)s * stage_pitch; };
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int B_FULL = 0, B_EMPTY = kD2Stages, B_ACC = 2 * kD2Stages;
+  const uint32_t tptr = bar0 + 8 * (2 * kD2Stages + 1);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + (tptr - sbase));
+  double* red = reinterpret_cast<double*>(smem_al + (tptr - sbase) + 16);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmWsh);
+    for (int i = 0; i < kD2Stages; ++i) { ptx::mbar_init(BAR(B_FULL + i), 1); ptx::mbar_init(BAR(B_EMPTY + i), 1); }
+    ptx::mbar_init(BAR(B_ACC), 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tptr, kR2N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const int b = blockIdx.z, cg = blockIdx.y, l0 = blockIdx.x * (8 * kR2N);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int r = 0; r < p.R; ++r) {
+        const int s = r % kD2Stages, ph = (r / kD2Stages) & 1;
+        ptx::mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+        ptx::mbar_expect_tx(BAR(B_FULL + s), (uint32_t)nkk * Smem::kTile + seg_bytes);
+        for (int kk = 0; kk < nkk; ++kk)
+          ptx::tma_load_2d(&tmWsh, BAR(B_FULL + s), STAGE(s) + kk * Smem::kTile, r * p.Tq + kk * kKB, cg * 128);
+        bulk_copy_g2s(STAGE(s) + nkk * Smem::kTile, p.Hp16 + ((int64_t)b * p.R + r) * p.Lp + p.padl - p.A8 + l0, seg_bytes,
+                      BAR(B_FULL + s));
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::idesc_f16(kM, kR2N, 0, 0);
+    constexpr uint32_t descHiA = ptx::smem_desc_hi_sw128(1024);
+    constexpr uint32_t descHiB = ((128u >> 4) & 0x3FFFu) | (1u << 14);      // SWIZZLE_NONE, 8-row groups 128 bytes apart
+    for (int r = 0; r < p.R; ++r) {
+      const int s = r % kD2Stages, ph = (r / kD2Stages) & 1;
+      if (lane == 0) ptx::mbar_wait(BAR(B_FULL + s), ph);
+      __syncwarp();
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t seg = STAGE(s) + nkk * Smem::kTile;
+        for (int kk = 0; kk < nkk; ++kk) {
+#pragma unroll
+          for (int ks = 0; ks < kKB / 16; ++ks) {
+            const uint32_t alo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
+            const uint32_t blo = ptx::smem_desc_lo(seg + (uint32_t)(kk * kKB + ks * 16) * 2, 16);
+            ptx::mma_ss(tmem, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc, (r | kk | ks) ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(BAR(B_EMPTY + s));
+        if (r == p.R - 1) ptx::mma_commit(BAR(B_ACC));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp & 3, m = q4 * 32 + lane;                 // TMEM lane = (c_local, s)
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int c = cg * 16 + (m >> 3), sph = m & 7;
+    const bool row_ok = c < p.C;
+    ptx::mbar_wait(BAR(B_ACC), 0);
+    ptx::tc_fence_after();
+    const float sc = exp2f(-(float)(p.exps[0] + p.exps[1]));
+    const float kap = *p.kappa, pscale = exp2f((float)p.exps[2]);
+    const float* vrow = p.V + ((int64_t)b * p.C + (row_ok ? c : 0)) * p.L;
+    __half* prow = p.P16out + ((int64_t)b * p.C + (row_ok ? c : 0)) * p.Lq;
+    double acc = 0.0;
+    // the 16 target values of chunk j + 1 are requested before chunk j is computed (one round trip per chunk, overlapped)
+    float v[16], vn[16];
+    auto load_v = [&](int j, float (&dst)[16]) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int l = l0 + 8 * (j * 16 + i) + sph;
+        dst[i] = (row_ok && l < p.L) ? __ldg(vrow + l) : 0.f;
+      }
+    };
+    load_v(0, vn);
+#pragma unroll 1
+    for (int j = 0; j < kR2N / 16; ++j) {
+      uint32_t sr[16];
+      ptx::tmem_ld16(tmem + lane_addr + j * 16, sr);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = vn[i];
+      if (j + 1 < kR2N / 16) load_v(j + 1, vn);
+      ptx::tc_wait_ld();
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int l = l0 + 8 * (j * 16 + i) + sph;
+        const bool ok = row_ok && l < p.L;
+        const float x = fmaf(__uint_as_float(sr[i]), sc, kEps);
+        if (LOSS) {
+          if (ok) a += v[i] * (__logf(v[i] + kEps) - __logf(x)) - v[i] + (x - kEps);         // metrics.py:22
+        } else if (row_ok && l < p.Lq) {
+          const float pv = ok ? fmaf(v[i], ptx::rcp_approx(x), -kap) * pscale : 0.f;         // nmf.py:65, centred
+          prow[l] = __float2half_rn(fminf(pv, 65504.f));
+        }
+      }
+      acc += (double)a;
+    }
+    if (LOSS) {
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) red[q4] = acc;
+      asm volatile("bar.sync 1, 128;");
+      if (q4 == 0 && lane == 0)
+        p.loss_part[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, kR2N);
+}
+
 // ---- operand preparation --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int pow2_exp14(float mx) {
   if (!(mx > 0.f) || !isfinite(mx)) return 0;
@@ -467,10 +616,12 @@ absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__
 //   Wr16[c][r Tp + tt]           = W[c, r, Tp - 1 - tt]        (recon: shifts reversed so that the H window ascends)
 //   Wf16[c][r Tp + tt]           = W[c, r, tt]                 (dgrad, Toeplitz-tile formulation)
 //   Ws16[(c, grp, r%16, s)][u]   = W[c, r, u - s]              (dgrad, eight shifted copies)
+//   Wsh16[(c, s)][r Tq + u]      = W[c, r, s + A8 - u]         (recon, eight shifted copies)
 __global__ void __launch_bounds__(256)
 prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, int ngroups,
               const unsigned int* __restrict__ absmax, int* __restrict__ exps, __half* __restrict__ Wr16,
-              __half* __restrict__ Wf16, __half* __restrict__ Ws16, float* __restrict__ cs_part) {
+              __half* __restrict__ Wf16, __half* __restrict__ Ws16, __half* __restrict__ Wsh16, int A8,
+              float* __restrict__ cs_part) {
   const int e = pow2_exp14(__uint_as_float(*absmax));
   if (blockIdx.x == 0 && threadIdx.x == 0) exps[0] = e;
   const float sc = exp2f((float)e);
@@ -500,6 +651,14 @@ prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = w_at(r, u + k - sh);
     *reinterpret_cast<uint4*>(Ws16 + ((int64_t)c * rows + n) * Tq + u) = pack8(v);
+  }
+  // recon, eight-phase formulation: Wsh16[(c, s)][r Tq + u] = W[c, r, s + A8 - u]
+  for (int i8 = threadIdx.x; i8 < 8 * R * Tq / 8; i8 += 256) {
+    const int i = i8 * 8, sh = i / (R * Tq), ru = i - sh * (R * Tq), r = ru / Tq, u = ru - r * Tq;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = w_at(r, sh + A8 - u - k);
+    *reinterpret_cast<uint4*>(Wsh16 + ((int64_t)c * 8 + sh) * ((int64_t)R * Tq) + ru) = pack8(v);
   }
   // per-component sums of this row: warp w takes r = w, w + 8, ...; fixed order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -619,7 +778,8 @@ int make_tmap2(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int
 struct TcNmfdState {
   NmfdShape d{};
   int Tp = 0, Lp = 0, padl = 0, Lq = 0, Cpad = 0;
-  __half *Wr16 = nullptr, *Wf16 = nullptr, *Hp16 = nullptr, *P16 = nullptr, *Ws16 = nullptr;
+  __half *Wr16 = nullptr, *Wf16 = nullptr, *Hp16 = nullptr, *P16 = nullptr, *Ws16 = nullptr, *Wsh16 = nullptr;
+  int A8 = 0;                       // T - 1 rounded up to 8: alignment of the H window of the eight-phase recon
   int Tq = 0, ngroups = 1, cps_h2 = 0, ws_h2 = 1;   // dgrad2: padded shift extent, 16-component groups, c per split, splits
   float* part = nullptr;            // wgrad / dgrad split partials
   int64_t part_floats = 0;
@@ -635,7 +795,7 @@ struct TcNmfdState {
   int loss_blocks = 0;
   int ws_w = 1, ws_h = 1;           // split counts of wgrad / dgrad
   int kbs_w = 0, kbs_h = 0;
-  CUtensorMap tmWr, tmWf, tmP, tmWs;
+  CUtensorMap tmWr, tmWf, tmP, tmWs, tmWsh;
   bool attr_set = false;
 };
 
@@ -645,7 +805,7 @@ bool tc_nmfd_supported(const NmfdShape& d, double beta) {
 
 void tc_nmfd_destroy(TcNmfdState* s) {
   if (!s) return;
-  cudaFree(s->Ws16); cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax); cudaFree(s->colsum); cudaFree(s->cs_part);
+  cudaFree(s->Wsh16); cudaFree(s->Ws16); cudaFree(s->Wr16); cudaFree(s->Wf16); cudaFree(s->Hp16); cudaFree(s->P16); cudaFree(s->part); cudaFree(s->absmax); cudaFree(s->colsum); cudaFree(s->cs_part);
   cudaFree(s->exps); cudaFree(s->kappa); cudaFree(s->vsum); cudaFree(s->loss_part);
   delete s;
 }
@@ -655,9 +815,10 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   TcNmfdState* s = new TcNmfdState();
   s->d = d;
   s->Tp = (int)round_up(d.T, kKB);
-  s->padl = (int)round_up(s->Tp + 136, 8);                       // every window start >= 0
-  s->Lp = (int)round_up((int64_t)s->padl + d.L + kWinHalfs + 136, 8);
-  s->Tq = (int)round_up(d.T + 7, kKB);
+  s->padl = (int)round_up(s->Tp + 136, 8);                       // every window start >= 0 (padl >= A8 as well)
+  s->Lp = (int)round_up((int64_t)s->padl + round_up((int64_t)d.L, 8 * kR2N) + 256 + kWinHalfs + 136, 8);
+  s->A8 = (int)round_up(d.T - 1, 8);
+  s->Tq = (int)round_up(s->A8 + 8, kKB);                            // shifts u in [0, A8 + 7]; also covers dgrad's [0, T + 6]
   s->ngroups = (int)ceil_div(d.R, 16);
   s->Lq = (int)round_up(round_up((int64_t)d.L, 2048) + 1024 + s->Tq + kWinHalfs + 8, 8);
   s->Cpad = (int)round_up(d.C, kM);
@@ -678,12 +839,15 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   const int hs = std::max(s->ws_h, s->ws_h2);
   const int64_t pw = (int64_t)s->ws_w * d.C * d.R * d.T, ph = (int64_t)hs * d.B * d.R * d.Lin;
   s->part_floats = pw > ph ? pw : ph;
-  s->loss_blocks = (int)(ceil_div(d.L, kM) * ceil_div(d.C, kM) * d.B);
+  s->loss_blocks = (int)std::max<int64_t>(ceil_div(d.L, kM) * ceil_div(d.C, kM) * d.B, ceil_div(d.L, 8 * kR2N) * ceil_div(d.C, 16) * d.B);
   const size_t wbytes = (size_t)s->Cpad * d.R * s->Tp * 2, hbytes = (size_t)d.B * d.R * s->Lp * 2;
   const size_t pbytes = ((size_t)d.B * d.C + 1) * s->Lq * 2;
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMalloc(&s->Wr16, wbytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->Wf16, wbytes);
+  const size_t wshbytes = (size_t)s->Cpad * 8 * d.R * s->Tq * 2;
+  if (e == cudaSuccess) e = cudaMalloc(&s->Wsh16, wshbytes);
+  if (e == cudaSuccess) e = cudaMemset(s->Wsh16, 0, wshbytes);
   const size_t wsbytes = (size_t)s->Cpad * s->ngroups * 128 * s->Tq * 2;
   if (e == cudaSuccess) e = cudaMalloc(&s->Ws16, wsbytes);
   if (e == cudaSuccess) e = cudaMemset(s->Ws16, 0, wsbytes);
@@ -717,6 +881,7 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
   rc |= make_tmap2(&s->tmWf, s->Wf16, (int64_t)s->Cpad * d.R, s->Tp, s->Tp, Rp16);
   rc |= make_tmap2(&s->tmP, s->P16, (int64_t)d.B * d.C, s->Lq, s->Lq, kM);
   rc |= make_tmap2(&s->tmWs, s->Ws16, (int64_t)s->Cpad * s->ngroups * 128, s->Tq, s->Tq, 128);
+  rc |= make_tmap2(&s->tmWsh, s->Wsh16, (int64_t)s->Cpad * 8, (int64_t)d.R * s->Tq, (int64_t)d.R * s->Tq, 128);
   if (rc) { tc_nmfd_destroy(s); return 2; }
   *out = s;
   return 0;
@@ -770,7 +935,7 @@ int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
       s->aw_valid = true;
     }
     prep_w_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->Tq, s->ngroups, s->absmax, s->exps, s->Wr16, s->Wf16,
-                                       s->Ws16, s->cs_part);
+                                       s->Ws16, s->Wsh16, s->A8, s->cs_part);
     NMF_LAUNCH_CHECK();
     fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.C, d.R, 1, s->colsum);
     NMF_LAUNCH_CHECK();
@@ -804,12 +969,38 @@ int tc_nmfd_recon(TcNmfdState* s, const float* V, const float* W, const float* H
                   cudaStream_t st) {
   int rc = refresh(s, W, H, st);
   if (rc) return rc;
+  static const bool v1 = getenv("NMFB200_NMFD_RECON1") != nullptr;      // A/B: the Toeplitz-tile formulation
+  const int nkk = s->Tq / kKB;
+  const uint32_t stage2 = (((uint32_t)nkk * Smem::kTile + (uint32_t)(8 * kR2N + s->Tq) * 2) + 1023u) & ~1023u;
+  const int smem2 = (int)(kD2Stages * stage2 + 8 * (2 * kD2Stages + 1) + 16 + 64 + 1024);
+  if (!v1 && smem2 <= 232448) {
+    const NmfdShape& d = s->d;
+    Recon2Params q{};
+    q.B = d.B; q.C = d.C; q.L = d.L; q.R = d.R; q.Lp = s->Lp; q.padl = s->padl; q.Lq = s->Lq; q.Tq = s->Tq; q.A8 = s->A8;
+    q.Hp16 = s->Hp16; q.P16out = s->P16; q.V = V; q.exps = s->exps; q.kappa = s->kappa; q.loss_part = s->loss_part;
+    static int attr0 = 0, attr1 = 0;
+    int& attr = loss ? attr1 : attr0;
+    if (smem2 > attr) {
+      if (loss) NMF_CUDA_CHECK(cudaFuncSetAttribute(tcnmfd_recon2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      else NMF_CUDA_CHECK(cudaFuncSetAttribute(tcnmfd_recon2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr = smem2;
+    }
+    dim3 grid2((unsigned)ceil_div(d.L, 8 * kR2N), (unsigned)ceil_div(d.C, 16), (unsigned)d.B);
+    if (loss) {
+      tcnmfd_recon2_kernel<true><<<grid2, kD2Threads, smem2, st>>>(s->tmWsh, q);
+      NMF_LAUNCH_CHECK();
+      return sum_partials(s->loss_part, (int)(grid2.x * grid2.y * grid2.z), loss_dev, st);
+    }
+    tcnmfd_recon2_kernel<false><<<grid2, kD2Threads, smem2, st>>>(s->tmWsh, q);
+    NMF_LAUNCH_CHECK();
+    return 0;
+  }
   NmfdTcParams p = base_params(s, V);
   dim3 grid((unsigned)ceil_div(s->d.L, kM), (unsigned)ceil_div(s->d.C, kM), (unsigned)s->d.B);
   if (loss) {
     rc = launch<kReconLoss>(s, s->tmWr, grid, p, st);
     if (rc) return rc;
-    return sum_partials(s->loss_part, s->loss_blocks, loss_dev, st);
+    return sum_partials(s->loss_part, (int)(grid.x * grid.y * grid.z), loss_dev, st);
   }
   return launch<kRecon>(s, s->tmWr, grid, p, st);
 }

@@ -37,10 +37,16 @@ apply_update_kernel(ApplyArgs a) {
     newv = p * mult;                                         // nmf.py:92
     a.param[idx] = newv;
   }
-  if (a.absmax_bits) {
+  if (a.absmax_bits) {          // one atomic per block: tens of thousands of same-address atomics serialise in L2
+    __shared__ float wmax[8];
     float m = newv;
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(a.absmax_bits, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
+      if (m > 0.f) atomicMax(a.absmax_bits, __float_as_uint(m));
+    }
   }
 }
 

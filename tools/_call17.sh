@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-cat > /tmp/nmfd_prof.py <<'PY'
+mkdir -p /tmp; cat > /tmp/nmfd_prof.py <<'PY'
 import os, sys
 sys.path[:0] = [os.getcwd(), os.path.join(os.getcwd(), "pytorch-nmf_b200")]
 import torch
