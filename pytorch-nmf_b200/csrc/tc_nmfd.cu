@@ -326,7 +326,7 @@ constexpr int kD2Stages = 2;     // per CTA; two CTAs per SM (one in its epilogu
 constexpr int kD2Q = 2;             // q tiles (accumulators) per CTA
 
 struct Dgrad2Params {
-  int B, C, R, Lin, Lq, Tq, ngroups;
+  int B, C, R, Lin, Lq, Tq, ngroups, nks;      // nks: 16-wide k-steps that carry shifts u <= T + 6
   const __half* P16;
   const int* exps;
   float* out;                       // [nsplit][B][R][Lin]
@@ -394,15 +394,12 @@ tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Param
       if (ptx::elect_one()) {
         for (int qt = 0; qt < kD2Q; ++qt) {
           const uint32_t seg = STAGE(s) + nkk * Smem::kTile + qt * seg_pitch;
-          for (int kk = 0; kk < nkk; ++kk) {
-#pragma unroll
-            for (int ks = 0; ks < kKB / 16; ++ks) {
-              // A: rows q = windows of the raw P row, 16 bytes apart; k-step = 16 elements = two core matrices 16 bytes apart
-              const uint32_t alo = ptx::smem_desc_lo(seg + (uint32_t)(kk * kKB + ks * 16) * 2, 16);
-              const uint32_t blo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
-              ptx::mma_ss(tmem + qt * 128, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc,
-                          (i | kk | ks) ? 1u : 0u);
-            }
+          for (int kst = 0; kst < p.nks; ++kst) {
+            const int kk = kst >> 2, ks = kst & 3;
+            // A: rows q = windows of the raw P row, 16 bytes apart; k-step = 16 elements = two core matrices 16 bytes apart
+            const uint32_t alo = ptx::smem_desc_lo(seg + (uint32_t)(kst * 16) * 2, 16);
+            const uint32_t blo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
+            ptx::mma_ss(tmem + qt * 128, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc, (i | kst) ? 1u : 0u);
           }
         }
         ptx::mma_commit(BAR(B_EMPTY + s));
@@ -457,7 +454,7 @@ tcnmfd_dgrad2_kernel(const __grid_constant__ CUtensorMap tmWs, const Dgrad2Param
 constexpr int kR2N = 256;
 
 struct Recon2Params {
-  int B, C, L, R, Lp, padl, Lq, Tq, A8;
+  int B, C, L, R, Lp, padl, Lq, Tq, A8, nks;   // nks: 16-wide k-steps that carry shifts u <= A8 + 7
   const __half* Hp16;
   __half* P16out;
   const float* V;
@@ -524,13 +521,11 @@ tcnmfd_recon2_kernel(const __grid_constant__ CUtensorMap tmWsh, const Recon2Para
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t seg = STAGE(s) + nkk * Smem::kTile;
-        for (int kk = 0; kk < nkk; ++kk) {
-#pragma unroll
-          for (int ks = 0; ks < kKB / 16; ++ks) {
-            const uint32_t alo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
-            const uint32_t blo = ptx::smem_desc_lo(seg + (uint32_t)(kk * kKB + ks * 16) * 2, 16);
-            ptx::mma_ss(tmem, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc, (r | kk | ks) ? 1u : 0u);
-          }
+        for (int kst = 0; kst < p.nks; ++kst) {
+          const int kk = kst >> 2, ks = kst & 3;
+          const uint32_t alo = ptx::smem_desc_lo(STAGE(s) + kk * Smem::kTile, 16) + 2 * ks;
+          const uint32_t blo = ptx::smem_desc_lo(seg + (uint32_t)(kst * 16) * 2, 16);
+          ptx::mma_ss(tmem, ptx::make_desc(alo, descHiA), ptx::make_desc(blo, descHiB), idesc, (r | kst) ? 1u : 0u);
         }
         ptx::mma_commit(BAR(B_EMPTY + s));
         if (r == p.R - 1) ptx::mma_commit(BAR(B_ACC));
@@ -621,12 +616,20 @@ __global__ void __launch_bounds__(256)
 prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, int ngroups,
               const unsigned int* __restrict__ absmax, int* __restrict__ exps, __half* __restrict__ Wr16,
               __half* __restrict__ Wf16, __half* __restrict__ Ws16, __half* __restrict__ Wsh16, int A8,
-              float* __restrict__ cs_part) {
+              float* __restrict__ cs_part, int use_smem) {
   const int e = pow2_exp14(__uint_as_float(*absmax));
   if (blockIdx.x == 0 && threadIdx.x == 0) exps[0] = e;
   const float sc = exp2f((float)e);
   const int c = blockIdx.x;
-  const float* Wc = W + (int64_t)c * R * T;
+  const float* Wg = W + (int64_t)c * R * T;
+  // this row of W (R x T fp32) is read ~20 times below: stage it in shared memory when it fits (dynamic: R T floats)
+  extern __shared__ float wrow[];
+  const float* Wc = Wg;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < R * T; i += 256) wrow[i] = Wg[i];
+    __syncthreads();
+    Wc = wrow;
+  }
   auto w_at = [&](int r, int t) { return (r < R && t >= 0 && t < T) ? Wc[r * T + t] * sc : 0.f; };
   auto pack8 = [&](const float (&v)[8]) {
     __half2 h[4];
@@ -635,7 +638,7 @@ prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, 
     return *reinterpret_cast<const uint4*>(h);
   };
   const int64_t rowlen = (int64_t)R * Tp;
-  for (int i8 = threadIdx.x; i8 < R * Tp / 8; i8 += 256) {
+  for (int i8 = threadIdx.x; Wr16 != nullptr && i8 < R * Tp / 8; i8 += 256) {
     const int i = i8 * 8, r = i / Tp, tt = i - r * Tp;
     float f[8], rv[8];
 #pragma unroll
@@ -786,6 +789,7 @@ struct TcNmfdState {
   unsigned int* absmax = nullptr;   // [2]: max of W, max of H (float bits; written by absmax_kernel or by the ratio stage)
   float* colsum = nullptr;          // [2][R]: colsum_W | colsum_H
   float* cs_part = nullptr;         // per-row / per-block partial sums of the factor being refreshed
+  bool need_tile_copies = false;    // Wr16 / Wf16 are in use (see refresh)
   bool w_fresh = false, h_fresh = false;      // the fp16 copies / column sums of W, H match the fp32 factor
   bool aw_valid = false, ah_valid = false;    // absmax[0], absmax[1] hold the max of the current W, H
   int* exps = nullptr;              // {eW, eH, eP}
@@ -874,6 +878,13 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
     set_error(std::string("tc_nmfd_create: ") + cudaGetErrorString(e));
     return 2;
   }
+  {
+    const int nkk = s->Tq / kKB;
+    const uint32_t st_r = (((uint32_t)nkk * Smem::kTile + (uint32_t)(8 * kR2N + s->Tq) * 2) + 1023u) & ~1023u;
+    const uint32_t st_d = (((uint32_t)nkk * Smem::kTile + kD2Q * ((((uint32_t)(1024 + s->Tq) * 2) + 127u) & ~127u)) + 1023u) & ~1023u;
+    const bool fits = kD2Stages * std::max(st_r, st_d) + 2048 <= 232448u;
+    s->need_tile_copies = !fits || getenv("NMFB200_NMFD_RECON1") != nullptr || getenv("NMFB200_NMFD_DGRAD1") != nullptr;
+  }
   int rc = 0;
   rc |= make_tmap2(&s->tmWr, s->Wr16, s->Cpad, (int64_t)d.R * s->Tp, (int64_t)d.R * s->Tp, kM);
   // dgrad reads Wf16 as (C R) rows of Tp columns, Rp16 rows per tile
@@ -934,8 +945,19 @@ int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
       NMF_LAUNCH_CHECK();
       s->aw_valid = true;
     }
-    prep_w_kernel<<<d.C, 256, 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->Tq, s->ngroups, s->absmax, s->exps, s->Wr16, s->Wf16,
-                                       s->Ws16, s->Wsh16, s->A8, s->cs_part);
+    // the reversed / forward copies are only read by the Toeplitz-tile kernels (A/B switches, or shifts too long for the
+    // eight-phase kernels' shared-memory stages)
+    const bool tile_copies = s->need_tile_copies;
+    const size_t wrow_bytes = (size_t)d.R * d.T * sizeof(float);
+    const int use_smem = wrow_bytes <= 200 * 1024 ? 1 : 0;
+    static size_t attr_bytes = 0;
+    if (use_smem && wrow_bytes > 48 * 1024 && wrow_bytes > attr_bytes) {
+      NMF_CUDA_CHECK(cudaFuncSetAttribute(prep_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wrow_bytes));
+      attr_bytes = wrow_bytes;
+    }
+    prep_w_kernel<<<d.C, 256, use_smem ? wrow_bytes : 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->Tq, s->ngroups, s->absmax, s->exps,
+                                                               tile_copies ? s->Wr16 : nullptr, s->Wf16, s->Ws16, s->Wsh16,
+                                                               s->A8, s->cs_part, use_smem);
     NMF_LAUNCH_CHECK();
     fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.C, d.R, 1, s->colsum);
     NMF_LAUNCH_CHECK();
@@ -977,6 +999,7 @@ int tc_nmfd_recon(TcNmfdState* s, const float* V, const float* W, const float* H
     const NmfdShape& d = s->d;
     Recon2Params q{};
     q.B = d.B; q.C = d.C; q.L = d.L; q.R = d.R; q.Lp = s->Lp; q.padl = s->padl; q.Lq = s->Lq; q.Tq = s->Tq; q.A8 = s->A8;
+    q.nks = (int)ceil_div(s->A8 + 8, 16);
     q.Hp16 = s->Hp16; q.P16out = s->P16; q.V = V; q.exps = s->exps; q.kappa = s->kappa; q.loss_part = s->loss_part;
     static int attr0 = 0, attr1 = 0;
     int& attr = loss ? attr1 : attr0;
@@ -1022,6 +1045,7 @@ int tc_nmfd_dgrad(TcNmfdState* s, const float** part, int* nsplit, cudaStream_t 
     Dgrad2Params q{};
     q.B = d.B; q.C = d.C; q.R = d.R; q.Lin = d.Lin; q.Lq = s->Lq; q.Tq = s->Tq; q.ngroups = s->ngroups;
     q.P16 = s->P16; q.exps = s->exps; q.out = s->part; q.c_per_split = s->cps_h2;
+    q.nks = (int)ceil_div(d.T + 7, 16);
     const int nkk = s->Tq / kKB;
     const uint32_t seg_pitch = (((uint32_t)(1024 + s->Tq) * 2) + 127u) & ~127u;
     const uint32_t stage = (((uint32_t)nkk * Smem::kTile + kD2Q * seg_pitch) + 1023u) & ~1023u;
