@@ -61,7 +61,7 @@ struct Smem {
   static constexpr int kToep = kStages * kTile;
   static constexpr int kWin = 2 * kStages * kTile;
   static constexpr int kBar = kWin + kStages * kWinHalfs * 2;
-  static constexpr int kNumBars = 3 * kStages + 1;           // win_full, tile_full, empty per stage + acc_full
+  static constexpr int kNumBars = 4 * kStages + 1;           // win_full, tile_full, empty, win_read per stage + acc_full
   static constexpr int kTmemPtr = kBar + 8 * kNumBars;
   static constexpr int kRed = kTmemPtr + 16;
   static constexpr int kTotal = kRed + 8 * 16;
@@ -86,7 +86,7 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
   uint8_t* smem_al = smem_raw + (sbase - raw32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto BAR = [&](int i) { return sbase + Smem::kBar + 8u * i; };
-  constexpr int B_WIN = 0, B_TILE = kStages, B_EMPTY = 2 * kStages, B_ACC = 3 * kStages;
+  constexpr int B_WIN = 0, B_TILE = kStages, B_EMPTY = 2 * kStages, B_WREAD = 3 * kStages, B_ACC = 4 * kStages;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_al + Smem::kTmemPtr);
   constexpr bool RECON = KIND == kRecon || KIND == kReconLoss;
   const int Rp16 = (p.R + 15) & ~15;
@@ -98,6 +98,7 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
       ptx::mbar_init(BAR(B_WIN + i), 1);
       ptx::mbar_init(BAR(B_TILE + i), 8);        // one arrival per producer warp
       ptx::mbar_init(BAR(B_EMPTY + i), 1);
+      ptx::mbar_init(BAR(B_WREAD + i), 8);       // the 8 producer warps have read the source window of this stage
     }
     ptx::mbar_init(BAR(B_ACC), 1);
     ptx::fence_barrier_init();
@@ -149,7 +150,8 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages, ph = (kb / kStages) & 1;
-        ptx::mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+        ptx::mbar_wait(BAR(B_EMPTY + s), ph ^ 1);      // the MMAs that read this stage's tiles have completed ...
+        ptx::mbar_wait(BAR(B_WREAD + s), ph ^ 1);      // ... and every producer warp has read its source window
         int px, py, e0; const __half* src;
         kblock(kb, px, py, src, e0);
         const uint32_t plain_bytes = KIND == kDgrad ? (uint32_t)Rp16 * kKB * 2 : (uint32_t)Smem::kTile;
@@ -212,7 +214,7 @@ tcnmfd_kernel(const __grid_constant__ CUtensorMap tmPlain, const NmfdTcParams p)
       }
       ptx::fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(BAR(B_TILE + s));
+      if (lane == 0) { ptx::mbar_arrive(BAR(B_TILE + s)); ptx::mbar_arrive(BAR(B_WREAD + s)); }
     }
     if (warp >= 8) {
       // =========================== epilogue (warps 8-11 = TMEM lane quarters 0-3) =====================================

@@ -12,7 +12,8 @@ There is no CPU compute path: `fit` on CPU-resident modules copies V / W / H to 
 device, runs there, and copies the factors back into the same Parameter storages ("host buffer"
 mode, the `e2e` number of bench.py).  Without a CUDA device or without the built library it raises.
 
-Out of scope: sparse targets, `sparse_fit`, NMF2D/NMF3D, PLCA, trainers.
+Sparse targets are accepted and densified on the device (no SDDMM kernel).  Out of scope:
+`sparse_fit`, NMF2D/NMF3D.  `trainer.BetaMu` and `plca.PLCA` live in their own modules.
 """
 import math
 import weakref
@@ -146,9 +147,16 @@ class BaseComponent(torch.nn.Module):
         dtype (nmf.py:214-218); here a float64 / half module (or target) is staged through fp32 copies and the result
         is written back into the same Parameter storages in their own dtype.
         """
-        if V.is_sparse:
-            raise NotImplementedError("sparse targets are outside the accelerated hot path; "
-                                      "use the reference implementation for them (SURVEY.md section 8 f3)")
+        sparse_target = V.is_sparse
+        if sparse_target:
+            # The reference's sparse derivation (nmf.py:95-119, :603-638: SDDMM at the non-zeros) is the same update as the
+            # dense one on V.to_dense() -- its own tests/test_nmf_sparse.py:8-37 asserts exactly that.  There is no SDDMM
+            # kernel here: the target is densified ON THE DEVICE and takes the fused dense path (memory = the dense size).
+            V = V.coalesce()
+            assert torch.all(V.values() >= 0.), "Target should be non-negative."            # nmf.py:329-330
+            if beta <= 0:                                                                    # nmf.py:332-336
+                raise ValueError("When beta <= 0 and V contains zeros, the training process may diverge. "
+                                 "Please add small values to V, or use a positive beta value.")
         W, H = self.W, self.H
         assert W is not None and H is not None, "fit() needs both W and H"
         self._check_target_shape(V)
@@ -161,7 +169,8 @@ class BaseComponent(torch.nn.Module):
             f32 = torch.float32
             on_gpu = W.device.type == "cuda"
             dev = W.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
-            Vd = V.to(dev, f32, non_blocking=True).contiguous()
+            Vd = V.to(dev, non_blocking=True)
+            Vd = (Vd.to_dense() if sparse_target else Vd).to(f32).contiguous()
             if on_gpu and W.dtype == f32 and H.dtype == f32:
                 Wd, Hd = W.data, H.data                       # updated in place, like param.data in the reference
             else:

@@ -375,3 +375,22 @@ def test_tc_frobenius_fit_matches_reference_golden(name):
     for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
         ok, err = _close(got, want, TC_RTOL, TC_ATOL_REL)
         assert ok, f"{name} {nm}: scaled err {err:.3e}"
+
+
+# ---- sparse targets (nmf.py:603-638): densified on the device; the reference's own check is sparse == dense ----------
+@pytest.mark.parametrize("beta", [0.5, 1, 1.5, 2, 3])
+@pytest.mark.parametrize("alpha,l1_ratio", [(0, 0), (0.1, 0.5)])
+def test_fit_sparse_dense_like_reference(beta, alpha, l1_ratio):
+    # reference tests/test_nmf_sparse.py:8-37
+    torch.manual_seed(7)
+    V = torch.rand(800, 800)
+    idx = torch.nonzero(V > 0.95).T
+    Vs = torch.sparse_coo_tensor(idx, V[idx[0], idx[1]], V.shape)
+    dense = NMF(V.shape, 16)
+    sparse = NMF(V.shape, 16)
+    sparse.load_state_dict(dense.state_dict())
+    dense, sparse = dense.cuda(), sparse.cuda()
+    n1 = dense.fit(Vs.to_dense().cuda(), beta, 0, 5, False, alpha, l1_ratio, precision="f32")
+    n2 = sparse.fit(Vs.cuda(), beta, 0, 5, False, alpha, l1_ratio, precision="f32")
+    assert n1 == n2
+    assert torch.allclose(dense.W, sparse.W) and torch.allclose(dense.H, sparse.H)

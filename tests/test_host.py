@@ -116,10 +116,14 @@ def test_fit_fails_loudly_without_cuda():
         m.fit(torch.rand(10, 8))
 
 
-def test_sparse_target_is_refused():
+def test_sparse_target_validation_like_reference():
+    # nmf.py:329-336: negative values and beta <= 0 are refused for sparse targets before any device work
     m = NMF((10, 8), 3)
-    with pytest.raises(NotImplementedError):
-        m.fit(torch.rand(10, 8).to_sparse())
+    V = torch.rand(10, 8).to_sparse()
+    with pytest.raises(ValueError, match="beta <= 0"):
+        m.fit(V, beta=0)
+    with pytest.raises(AssertionError, match="non-negative"):
+        m.fit((-torch.rand(10, 8)).to_sparse())
 
 
 # ---- fit() host logic against the reference's outputs, with the oracle standing in for the GPU ----
