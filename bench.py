@@ -67,14 +67,15 @@ def ncu_traffic(precision, cfg_name):
     for rnd in ("r2", "r1"):
         rel = os.path.join("profiles", f"{rnd}_ncu_tc_contract_{precision}.txt")
         try:
-            tot = 0.0
+            tot, launches = 0.0, 0
             for ln in open(os.path.join(ROOT, rel)):
                 ln = ln.strip()
                 if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
                     val, unit = ln.split("=")[1].split()[:2]
                     tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+                    launches += ln.startswith("dram__bytes_read.sum")
             if tot:
-                return tot, rel
+                return tot / max(launches, 1), rel      # the capture may hold the W and the H launch: per-launch mean
         except Exception:
             continue
     return None, None

@@ -116,3 +116,21 @@ def test_heavy_tailed_target_default_precision_matches_reference(beta):
     n = m.fit(V.cuda(), beta, float("-inf"), int(c["max_iter"]))
     assert n == int(c["n_iter"])
     _compare(c, m, f"heavy beta={beta} [{m.last_fit_precision}]")
+
+
+def test_nmfd_tensor_core_fit_is_bitwise_repeatable():
+    """Two fits from the same state give identical bits: every reduction of the tensor-core NMFD path runs in a fixed
+    order (split partials summed in order, the only atomics are integer max), and the shared-memory windows are handed
+    over by mbarriers -- a lost ordering there would show up here as run-to-run differences."""
+    torch.manual_seed(3)
+    V = torch.rand(2, 130, 700).cuda()
+    W0 = torch.rand(130, 5, 37)
+    H0 = torch.rand(2, 5, 700 - 37 + 1)
+    outs = []
+    for _ in range(3):
+        m = NMFD(W=W0.clone(), H=H0.clone()).cuda()
+        m.fit(V, 1, float("-inf"), 12)
+        assert m.last_fit_precision == "f16"
+        outs.append((m.W.data.clone(), m.H.data.clone()))
+    for W, H in outs[1:]:
+        assert torch.equal(W, outs[0][0]) and torch.equal(H, outs[0][1])

@@ -26,7 +26,8 @@ for r in rows[2:]:
     st.sort(key=lambda x: -x[1])
     for h, v in st[:8]:
         print(f"   stall {h.replace('smsp__average_warps_issue_stalled_','').replace('_per_issue_active.ratio','')}: {v:.2f}")
-    break
-if len(sys.argv) > 2:
+    if "--all" not in sys.argv:
+        break
+if len(sys.argv) > 2 and "--all" not in sys.argv:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     print(src[:3000])
