@@ -83,9 +83,9 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
   long long t0 = 0;
 #ifdef NMFB200_TRACE
   const unsigned int mode = *reinterpret_cast<volatile unsigned int*>(&g_tune_park);
-  const bool park = mode == 1u;
+  const bool park = mode != 2u;            // tuning build: NMFB200_TC_PARK=2 restores the plain poll loop
 #else
-  constexpr bool park = false;
+  constexpr bool park = true;       // parked polls: +1 % sustained at cfg2 (power-capped part), nothing in a burst
   constexpr unsigned int mode = 0u;
 #endif
   while (!(park ? mbar_try_wait_parked(bar, parity) : mbar_try_wait(bar, parity))) {

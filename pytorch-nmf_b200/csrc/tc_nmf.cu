@@ -48,6 +48,8 @@ constexpr uint32_t kColS = 0;        // S/P stages: columns [TN i, TN i + TN); O
 //   NP    0: the ratio tile P is written over the S columns of its stage (the stage is free again when the O-MMA has
 //         consumed P).  > 0: P has NP buffers of TN / 2 columns of its own: an S stage is handed back as soon as the
 //         ratio warps have READ it, a P buffer when its O-MMA has completed -- two short rings instead of one long one.
+constexpr unsigned kEpiPaceNs = 100;     // pause between the epilogue's row stores (see the epilogue warpgroup)
+
 template <int RP_, bool SPLIT_, int TN_, int NF_, int NG_, int NV_, int NS_, int NRW_ = 2, int NP_ = 0>
 struct Cfg {
   static constexpr int RP = RP_, TN = TN_, NF = NF_, NG = NG_, NV = NV_, NS = NS_, NRW = NRW_, NP = NP_;
@@ -71,7 +73,7 @@ struct TcKernelParams {
   double* loss_part;          // LOSS mode: [gridDim.x][2] = {sum v~ lg2(x), sum S~}
   const float* kappa;         // device scalar: centring constant of the ratio tile (typical P), 0 = off
   int pf_dist;                // L2 prefetch distance of the V stream in tiles (0 = off)
-  long long* trace;           // tuning aid: per-tile event timestamps of CTA 0 ([tile][12]), or nullptr
+  long long* trace;           // tuning aid: per-tile event timestamps of CTA 0 ([tile][16]), or nullptr
   int knock;                  // tuning build only (NMFB200_TC_KNOCK): bit mask of pipeline stages to skip
 };
 
@@ -80,7 +82,7 @@ struct TcKernelParams {
 #ifdef NMFB200_TRACE
 #define TC_TRACE(tile, k)                                                        \
   do {                                                                         \
-    if (p.trace && blockIdx.x == 0 && (tile) < 256) p.trace[(tile) * 12 + (k)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && (tile) < 256) p.trace[(tile) * 16 + (k)] = clock64(); \
   } while (0)
 #define TC_KNOCK(bit) ((p.knock & (bit)) != 0)      // knock-out experiments (results invalid): which stage bounds the kernel?
 #else
@@ -277,6 +279,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
           if (lane == 0) {
             TC_TRACE(ts, 0);
             ptx::mbar_wait(BAR(B_GFULL + sg), sg_ph);              // G tile landed
+            TC_TRACE(ts, 12);
             // the stage is free: the O-MMA of the tile NS earlier consumed its P (alias layout) / the ratio warps have
             // read the S of the tile NS earlier (P buffers of their own)
             ptx::mbar_wait(BAR((PSEP && !LOSS ? B_SEMPTY : B_PEMPTY) + ss), ss_ph ^ 1);
@@ -301,6 +304,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             }
             ptx::mma_commit(BAR(B_SFULL + ss));
             if (j == n - 1) ptx::mma_commit(BAR(B_FEMPTY + f_s));  // last S of the item: its F block is free
+            TC_TRACE(ts, 13);
           }
           __syncwarp();
           if (++sg == NG) { sg = 0; sg_ph ^= 1; }
@@ -353,10 +357,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
                 if (TWO)
                   ptx::mma_ts(tmem + kColO2, tmem + kColPp + os * 64 + ks * 8, ptx::make_desc(blo + ks * 128, descHi),
                               idescO, (first && ks == 0) ? 0u : 1u);
+                if (ks == 0) TC_TRACE(to, 15);
               }
               ptx::mma_commit(BAR(B_GEMPTY + og));     // G tile free (its S-MMA finished before the ratio tile existed)
               ptx::mma_commit(BAR(B_PEMPTY + os));     // S/P stage free
               if (last) ptx::mma_commit(BAR(B_OFULL));
+              TC_TRACE(to, 14);
             }
           }
           __syncwarp();
@@ -513,6 +519,14 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         for (int cc = 0; cc < kCpw; cc += 2) {
           const int c = c_lo + cc;
           const bool lastpair = cc + 2 >= kCpw;
+          // The next tile's full barriers are TESTED a chunk of work before they are needed: a try_wait returns its answer
+          // after ~100 cycles even when the phase completed long ago (ncu source page: 15 % of the ratio warps' time sat on
+          // the two polls of every tile), and both ratio warps of a sub-partition reach them together.
+          bool okV = false, okS = false;
+          if (lastpair && more) {
+            okV = ptx::mbar_test_wait(BAR(B_VFULL + sv1), phV1);
+            okS = ptx::mbar_test_wait(BAR(B_SFULL + st1), phS1);
+          }
           ptx::tc_wait_ld();
           load_chunk(tS, vT, c + 1, sB, vB);
           compute_chunk(tS, tP, c, sA, vA);
@@ -530,9 +544,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             }
             if (more) {
               if (g == 0 && q == 0 && lane == 0) TC_TRACE(tt + 1, 2);
-              ptx::mbar_wait(BAR(B_VFULL + sv1), phV1);
+              if (!okV) ptx::mbar_wait(BAR(B_VFULL + sv1), phV1);
               if (g == 0 && q == 0 && lane == 0) TC_TRACE(tt + 1, 3);
-              ptx::mbar_wait(BAR(B_SFULL + st1), phS1);
+              if (!okS) ptx::mbar_wait(BAR(B_SFULL + st1), phS1);
               if (g == 0 && q == 0 && lane == 0) TC_TRACE(tt + 1, 4);
               ptx::tc_fence_after();
               load_chunk(tS1, vT1, c_lo, sA, vA);
@@ -751,10 +765,18 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(BAR(B_OEMPTY));
+        // Each lane owns a row, so one store instruction touches 32 cache lines = 32 passes through the load/store unit
+        // that the ratio warps' shared-memory loads (and every other memory instruction of the SM) queue behind: issued
+        // back to back, the 64 stores of an item stopped the whole SM for ~2300 cycles at every item boundary (per-tile
+        // trace: 9 % of the launch).  Nothing waits for these stores (the next epilogue is 16 tiles away): pace them.
         if (grow < p.Mr) {
 #pragma unroll
-          for (int i = 0; i < 64; i += 4)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          for (int i = 0; i < 64; i += 8) {          // 256-bit stores: half the instructions, half the passes
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"l"(dst + i), "f"(o[i]), "f"(o[i + 1]), "f"(o[i + 2]), "f"(o[i + 3]), "f"(o[i + 4]), "f"(o[i + 5]),
+                           "f"(o[i + 6]), "f"(o[i + 7]) : "memory");
+            __nanosleep(kEpiPaceNs);
+          }
         }
         continue;
       }
@@ -1592,12 +1614,12 @@ int tc_create(TcState** out, int device, int64_t N, int64_t C, int64_t R, bool s
   if (const char* e = getenv("NMFB200_TC_PF")) s->pf_dist = atoi(e);
   if (const char* e = getenv("NMFB200_TC_KNOCK")) s->knock = atoi(e);
   {
-    const unsigned int park = getenv("NMFB200_TC_PARK") ? (unsigned)atoi(getenv("NMFB200_TC_PARK")) : 0u;   // 1 = parked polls, >= 2 = nanosleep(n) back-off
+    const unsigned int park = getenv("NMFB200_TC_PARK") ? (unsigned)atoi(getenv("NMFB200_TC_PARK")) : 0u;   // default: parked polls; 2 = plain poll loop; > 2 = nanosleep(n) back-off
     cudaMemcpyToSymbol(ptx::g_tune_park, &park, sizeof(park));
   }
   if (const char* e = getenv("NMFB200_TC_TRACE")) {
     s->trace_path = e;
-    if (cudaMalloc(&s->trace, 256 * 12 * sizeof(long long)) != cudaSuccess) s->trace = nullptr;
+    if (cudaMalloc(&s->trace, 256 * 16 * sizeof(long long)) != cudaSuccess) s->trace = nullptr;
   }
 #endif
   s->ldc = round_up(C, 8);
@@ -1841,7 +1863,7 @@ int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   p.trace = s->trace;
   p.knock = s->knock;
   p.pf_dist = s->pf_dist;
-  if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 12 * sizeof(long long), st);
+  if (s->trace) cudaMemsetAsync(s->trace, 0, 256 * 16 * sizeof(long long), st);
   const int items = pl.row_blocks * pl.nchunks;
   const int grid = items < s->num_sms ? items : s->num_sms;
   if (which == 0)
@@ -2055,12 +2077,12 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
     if (tc_check_wait_abort(st) > 0) { set_error("mbarrier wait aborted (protocol bug)"); return 2; }
   }
   if (rc == 0 && s->trace) {
-    std::vector<long long> h(256 * 12);
+    std::vector<long long> h(256 * 16);
     cudaMemcpyAsync(h.data(), s->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     if (FILE* f = fopen(s->trace_path.c_str(), "w")) {
       for (int t = 0; t < 256; ++t) {
-        for (int k = 0; k < 12; ++k) fprintf(f, "%lld ", h[t * 12 + k]);
+        for (int k = 0; k < 16; ++k) fprintf(f, "%lld ", h[t * 16 + k]);
         fprintf(f, "\n");
       }
       fclose(f);

@@ -18,8 +18,8 @@ for _ in range(3): eng.contract_only(which, 1.0)
 torch.cuda.synchronize()
 rows = [[int(x) for x in l.split()] for l in open(os.environ["NMFB200_TC_TRACE"])]
 t0 = min(x for r in rows for x in r if x > 0)
-names = ["S:wait_g", "S:got_g", "R:prewait", "R:gotV", "R:gotS", "O:wait_p", "O:got_p", "V:issue", "G:issue", "R:end00", "R:lastcmp", "R:endN3"]
+names = ["S:wait_g", "S:got_g", "R:prewait", "R:gotV", "R:gotS", "O:wait_p", "O:got_p", "V:issue", "G:issue", "R:end00", "R:lastcmp", "R:endN3", "S:gotG", "S:issued", "O:issued", "O:mma0"]
 print("tile " + " ".join(n.rjust(9) for n in names))
 for i, r in enumerate(rows[:64]):
     if not any(r): break
-    print(f"{i:4d} " + " ".join((str(x - t0) if x else "-").rjust(9) for x in r[:12]))
+    print(f"{i:4d} " + " ".join((str(x - t0) if x else "-").rjust(9) for x in r[:16]))
