@@ -135,6 +135,12 @@ int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, 
 /* Sizes as NMFD.__init__ (nmf.py:762-774): V (B,C,L), W (C,R,T), H (B,R,L-T+1). */
 int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int64_t L,
                         int64_t R, int64_t T, int precision);
+/* NMF2D / NMF3D (nmf.py:782-865, :868-942: conv2d / conv3d with flipped kernels and full padding): the same context type
+ * with ndim = 2 or 3 convolved axes.  vdims = the target's sizes over those axes, kdims = kernel_size; V (B,C,*vdims),
+ * W (C,R,*kdims), H (B,R,*(vdims - kdims + 1)), all contiguous.  ndim = 1 is nmfb200_nmfd_create.  Every nmfb200_nmfd_*
+ * call below serves these contexts; they run on the fp32 kernels (precision auto or f32). */
+int nmfb200_nmfnd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int ndim, const int64_t* vdims,
+                         int64_t R, const int64_t* kdims, int precision);
 int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream);
 int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H,
                           double beta, double gamma, double l1_reg, double l2_reg, void* stream);

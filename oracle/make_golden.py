@@ -270,6 +270,38 @@ def next_row_cases():
     print(f"wrote reference_next.npz ({os.path.getsize(os.path.join(GOLD, 'reference_next.npz')) / 1e6:.2f} MB)")
 
 
+def nd_cases():
+    """NMF2D / NMF3D (nmf.py:782-942): ragged sizes, every beta branch, penalties, a batch of 2 and a frozen factor."""
+    torch.set_num_threads(1)
+    cases = {}
+    specs = [("nmf2d", ref_nmf.NMF2D, (2, 5, 17, 23), 4, (3, 4)),
+             ("nmf3d", ref_nmf.NMF3D, (1, 3, 9, 10, 21), 3, (2, 3, 5))]
+    for kind, cls, vs, R, K in specs:
+        B, C, X = vs[0], vs[1], vs[2:]
+        hs = (B, R) + tuple(x - k + 1 for x, k in zip(X, K))
+        for beta in (0, 0.5, 1, 1.5, 2, 3):
+            for alpha, l1r in ((0, 0), (0.1, 0.5)):
+                V, W0, H0 = make_inputs(vs, (C, R) + K, hs, floor=2 ** -7 if beta <= 0 else 0.0)
+                W, H, n_iter, losses = run_reference(cls, V, W0, H0, beta, float("-inf"), 20, alpha, l1r)
+                cases[f"{kind}_b{beta}_a{alpha}_l{l1r}"] = dict(
+                    kind=kind, V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                    beta=beta, tol=float("-inf"), max_iter=20, alpha=alpha, l1_ratio=l1r)
+        V, W0, H0 = make_inputs(vs, (C, R) + K, hs)
+        W, H, n_iter, losses = run_reference(cls, V, W0, H0, 1, 1e-3, 60, 0, 0)
+        cases[f"{kind}_stoprule"] = dict(kind=kind, V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                         beta=1, tol=1e-3, max_iter=60, alpha=0, l1_ratio=0)
+        W, H, n_iter, losses = run_reference(cls, V, W0, H0, 2, float("-inf"), 10, 0, 0, trainable_H=False)
+        cases[f"{kind}_frozenH"] = dict(kind=kind, V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                        beta=2, tol=float("-inf"), max_iter=10, alpha=0, l1_ratio=0, trainable_H=False)
+    # a kernel longer than one 32-wide shift chunk of the sliding axis, and outer axes longer than the kernel's
+    vs, R, K = (1, 70, 6, 150), 5, (2, 37)
+    V, W0, H0 = make_inputs(vs, (70, R) + K, (1, R, 5, 114))
+    W, H, n_iter, losses = run_reference(ref_nmf.NMF2D, V, W0, H0, 1, float("-inf"), 10, 0, 0)
+    cases["nmf2d_long_kernel"] = dict(kind="nmf2d", V=V, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                      beta=1, tol=float("-inf"), max_iter=10, alpha=0, l1_ratio=0)
+    save_cases(cases, "reference_nd.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg2", action="store_true")
@@ -277,8 +309,12 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--r2", action="store_true", help="only the round-2 fixtures (reference_r2.npz)")
     ap.add_argument("--next-rows", action="store_true", help="only the BetaMu / PLCA fixtures (reference_next.npz)")
+    ap.add_argument("--nd", action="store_true", help="only the NMF2D / NMF3D fixtures (reference_nd.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.nd:
+        nd_cases()
+        sys.exit(0)
     if a.next_rows:
         next_row_cases()
         sys.exit(0)

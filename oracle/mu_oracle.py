@@ -179,6 +179,70 @@ def nmfd_update_h(V, W, H, beta, gamma=None, l1_reg=0.0, l2_reg=0.0):
 
 
 # --------------------------------------------------------------------------------------
+# NMF2D / NMF3D  (V (B,C,*X), W (C,R,*K), H (B,R,*J), X = J + K - 1 per axis; nmf.py:782-942)
+# The same three contractions as NMFD with a multi-index shift: one term per kernel offset.
+# --------------------------------------------------------------------------------------
+def _offsets(K):
+    import itertools
+    return itertools.product(*(range(k) for k in K))
+
+
+def _window(t, J):
+    return (slice(None), slice(None)) + tuple(slice(ti, ti + j) for ti, j in zip(t, J))
+
+
+def nmfnd_reconstruct(H, W):
+    """nmf.py:861-865 (conv2d) / :938-942 (conv3d), flipped kernel + full padding, restated as shifted products:
+    WH[b,c,j+t] += sum_r W[c,r,t] H[b,r,j]."""
+    J, K = H.shape[2:], W.shape[2:]
+    out = torch.zeros(H.shape[0], W.shape[0], *(j + k - 1 for j, k in zip(J, K)), dtype=H.dtype)
+    for t in _offsets(K):
+        out[_window(t, J)] += torch.einsum("cr,br...->bc...", W[(slice(None), slice(None)) + t], H)
+    return out
+
+
+def nmfnd_grad_w(G, H, K):
+    """gW[c,r,t] = sum_{b,j} G[b,c,j+t] H[b,r,j]."""
+    J = H.shape[2:]
+    gW = torch.zeros(G.shape[1], H.shape[1], *K, dtype=H.dtype)
+    for t in _offsets(K):
+        gW[(slice(None), slice(None)) + t] = torch.einsum("bc...,br...->cr", G[_window(t, J)], H)
+    return gW
+
+
+def nmfnd_grad_h(G, W, J):
+    """gH[b,r,j] = sum_{c,t} W[c,r,t] G[b,c,j+t]."""
+    K = W.shape[2:]
+    gH = torch.zeros(G.shape[0], W.shape[1], *J, dtype=W.dtype)
+    for t in _offsets(K):
+        gH += torch.einsum("cr,bc...->br...", W[(slice(None), slice(None)) + t], G[_window(t, J)])
+    return gH
+
+
+def _sum_but_rank(x):
+    dims = [d for d in range(x.dim()) if d != 1]
+    return x.sum(dims, keepdim=True)                               # nmf.py:122-131
+
+
+def nmfnd_update_w(V, W, H, beta, gamma=None, l1_reg=0.0, l2_reg=0.0):
+    gamma = gamma_of(beta) if gamma is None else gamma
+    K = tuple(W.shape[2:])
+    Pn, Pp = phi(V, nmfnd_reconstruct(H, W), beta)
+    num = nmfnd_grad_w(Pn, H, K)
+    den = _sum_but_rank(H) if beta == 1 else nmfnd_grad_w(Pp, H, K)             # (1,R,1,..) broadcasts over W
+    return _ratio_update(W, num, den, gamma, l1_reg, l2_reg, beta == 1)
+
+
+def nmfnd_update_h(V, W, H, beta, gamma=None, l1_reg=0.0, l2_reg=0.0):
+    gamma = gamma_of(beta) if gamma is None else gamma
+    J = tuple(H.shape[2:])
+    Pn, Pp = phi(V, nmfnd_reconstruct(H, W), beta)
+    num = nmfnd_grad_h(Pn, W, J)
+    den = _sum_but_rank(W).squeeze(0) if beta == 1 else nmfnd_grad_h(Pp, W, J)  # (R,1,..) broadcasts over H
+    return _ratio_update(H, num, den, gamma, l1_reg, l2_reg, beta == 1)
+
+
+# --------------------------------------------------------------------------------------
 # fit loop (nmf.py:298-409)
 # --------------------------------------------------------------------------------------
 def fit(V, W, H, beta=1, tol=1e-4, max_iter=200, alpha=0, l1_ratio=0,
@@ -192,6 +256,8 @@ def fit(V, W, H, beta=1, tol=1e-4, max_iter=200, alpha=0, l1_ratio=0,
     recon, upd_w, upd_h = {
         "nmf": (nmf_reconstruct, nmf_update_w, nmf_update_h),
         "nmfd": (nmfd_reconstruct, nmfd_update_w, nmfd_update_h),
+        "nmf2d": (nmfnd_reconstruct, nmfnd_update_w, nmfnd_update_h),
+        "nmf3d": (nmfnd_reconstruct, nmfnd_update_w, nmfnd_update_h),
     }[kind]
     gamma = gamma_of(beta)
     l1_reg = alpha * l1_ratio                                                   # :348

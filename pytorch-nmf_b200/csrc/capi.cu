@@ -431,15 +431,27 @@ int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, 
 
 /* ---- NMFD ------------------------------------------------------------------------------------ */
 
-int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int64_t L, int64_t R, int64_t T,
-                        int precision) {
+// One context type serves NMFD (one sliding axis) and NMF2D / NMF3D (the last axis slides, the outer ones are loops):
+// vdims / kdims hold the target's and the kernel's sizes over the ndim convolved axes.
+static int nmfd_create_impl(nmfb200_ctx** out, int device, int64_t B, int64_t C, int ndim, const int64_t* vdims,
+                            int64_t R, const int64_t* kdims, int precision) {
   if (!out) return fail(NMFB200_ERR_INVALID, "out is null");
   *out = nullptr;
-  if (B < 1 || C < 1 || R < 1 || T < 1 || L < T) return fail(NMFB200_ERR_INVALID, "bad NMFD sizes");
+  if (ndim < 1 || ndim > 3 || !vdims || !kdims) return fail(NMFB200_ERR_INVALID, "1 to 3 convolved axes are supported");
+  int64_t X[3] = {1, 1, 1}, K[3] = {1, 1, 1};            // right-aligned: X[2] / K[2] is the last (sliding) axis
+  for (int i = 0; i < ndim; ++i) { X[3 - ndim + i] = vdims[i]; K[3 - ndim + i] = kdims[i]; }
+  const int64_t L = X[2], T = K[2];
+  if (B < 1 || C < 1 || R < 1) return fail(NMFB200_ERR_INVALID, "bad NMFD sizes");
+  for (int i = 0; i < 3; ++i)
+    if (K[i] < 1 || X[i] < K[i]) return fail(NMFB200_ERR_INVALID, "bad NMFD sizes");
   if (R > 256) return fail(NMFB200_ERR_INVALID, "rank > 256 is not supported");
   if (precision != NMFB200_PREC_AUTO && precision != NMFB200_PREC_F32 && precision != NMFB200_PREC_F16)
     return fail(NMFB200_ERR_INVALID, "NMFD precision must be auto, f32 or f16");
-  if (B * C * L > (int64_t)1 << 40) return fail(NMFB200_ERR_INVALID, "NMFD target too large");
+  if (B * C * X[0] * X[1] * L > (int64_t)1 << 40 || X[0] * X[1] * L > (int64_t)1 << 30 || K[0] * K[1] * T > (int64_t)1 << 24)
+    return fail(NMFB200_ERR_INVALID, "NMFD target too large");
+  const bool one_d = X[0] == 1 && X[1] == 1;
+  if (!one_d && precision == NMFB200_PREC_F16)
+    return fail(NMFB200_ERR_INVALID, "NMF2D / NMF3D run on the fp32 kernels (precision auto or f32)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(NMFB200_ERR_CUDA, "cannot select the requested device");
   nmfb200_ctx* c = new (std::nothrow) nmfb200_ctx();
@@ -447,12 +459,13 @@ int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int
   c->kind = 1; c->device = device; c->precision = precision == NMFB200_PREC_F32 ? NMFB200_PREC_F32 : NMFB200_PREC_F16; c->R = R;
   c->auto_mode = precision == NMFB200_PREC_AUTO;
   c->d = NmfdShape{(int)B, (int)C, (int)L, (int)R, (int)T, (int)(L - T + 1)};
+  c->d.X1 = (int)X[0]; c->d.X2 = (int)X[1]; c->d.T1 = (int)K[0]; c->d.T2 = (int)K[1];
   c->dgrad_nsplit = nmfd_dgrad_nsplit(c->d);
-  int64_t pf = C * R * T;
-  int64_t hf = (int64_t)c->dgrad_nsplit * B * R * c->d.Lin;
+  int64_t pf = C * R * c->d.w_inner();
+  int64_t hf = (int64_t)c->dgrad_nsplit * B * R * c->d.h_inner();
   if (hf > pf) pf = hf;
   c->part_floats = pf;
-  int64_t cs1 = colsum_scratch_floats(C, (int)R, T), cs2 = colsum_scratch_floats(B, (int)R, c->d.Lin);
+  int64_t cs1 = colsum_scratch_floats(C, (int)R, c->d.w_inner()), cs2 = colsum_scratch_floats(B, (int)R, c->d.h_inner());
   c->cs_scratch_floats = cs1 > cs2 ? cs1 : cs2;
   c->loss_max_blocks = nmfd_max_blocks(c->d);
   cudaError_t e = cudaSuccess;
@@ -461,12 +474,12 @@ int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int
   if (e == cudaSuccess) e = cudaMalloc(&c->cs_scratch, c->cs_scratch_floats * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&c->loss_blocks, (size_t)c->loss_max_blocks * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&c->mm_scratch, 2050 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&c->Pn, (size_t)B * C * L * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->Pn, (size_t)B * C * c->d.v_inner() * sizeof(float));
   if (e != cudaSuccess) {
     free_ctx(c);
     return fail(NMFB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   }
-  if (c->precision != NMFB200_PREC_F32) {
+  if (c->precision != NMFB200_PREC_F32 && one_d) {       // the tensor-core kernels cover the one-axis case
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.major == 10) {
       int rc = tc_nmfd_create(&c->tcd, c->d);          // beta = 1 runs as tcgen05 sliding GEMMs (tc_nmfd.cu)
@@ -480,12 +493,23 @@ int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int
   return 0;
 }
 
+int nmfb200_nmfd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int64_t L, int64_t R, int64_t T,
+                        int precision) {
+  return nmfd_create_impl(out, device, B, C, 1, &L, R, &T, precision);
+}
+
+int nmfb200_nmfnd_create(nmfb200_ctx** out, int device, int64_t B, int64_t C, int ndim, const int64_t* vdims,
+                         int64_t R, const int64_t* kdims, int precision) {
+  return nmfd_create_impl(out, device, B, C, ndim, vdims, R, kdims, precision);
+}
+
 int nmfb200_nmfd_set_target(nmfb200_ctx* ctx, const float* V, void* stream) {
   CTX_GUARD(ctx, 1);
   if (!V) return fail(NMFB200_ERR_INVALID, "null target");
   ctx->V = V; ctx->has_target = true;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = matrix_minmax(V, (int64_t)ctx->d.B * ctx->d.C, ctx->d.L, ctx->d.L, ctx->mm_scratch, ctx->mm_scratch + 2048, st);
+  const int64_t vin = ctx->d.v_inner();
+  int rc = matrix_minmax(V, (int64_t)ctx->d.B * ctx->d.C, vin, vin, ctx->mm_scratch, ctx->mm_scratch + 2048, st);
   if (rc) return rc;
   ctx->tc_off = false;
   if (ctx->tcd) {
@@ -514,7 +538,7 @@ static int nmfd_tc_recon(nmfb200_ctx* c, const float* W, const float* H, bool lo
 
 static int nmfd_phi(nmfb200_ctx* c, const float* W, const float* H, double beta, cudaStream_t st) {
   if (beta != 1.0) {
-    if (!c->Pp) NMF_CUDA_CHECK(cudaMalloc(&c->Pp, (size_t)c->d.B * c->d.C * c->d.L * sizeof(float)));
+    if (!c->Pp) NMF_CUDA_CHECK(cudaMalloc(&c->Pp, (size_t)c->d.B * c->d.C * c->d.v_inner() * sizeof(float)));
     int e = ensure_den(c);
     if (e) return e;
   }
@@ -551,13 +575,13 @@ int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double bet
   float* kl = nullptr;
   if (beta == 1.0) {
     kl = ctx->colsum + d.R;
-    rc = factor_colsum(H, d.B, d.R, d.Lin, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);   // nmf.py:122-125
+    rc = factor_colsum(H, d.B, d.R, d.h_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);   // nmf.py:122-125
   } else {
     rc = nmfd_wgrad(d, ctx->Pp, H, ctx->den, st);
   }
   if (rc) return rc;
   ApplyArgs a{};
-  a.param = W; a.numel = (int64_t)d.C * d.R * d.T; a.R = d.R; a.inner = d.T; a.rowlen = (int64_t)d.R * d.T;
+  a.param = W; a.numel = (int64_t)d.C * d.R * d.w_inner(); a.R = d.R; a.inner = d.w_inner(); a.rowlen = (int64_t)d.R * d.w_inner();
   a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = 1; a.chunk_stride = 0;
   a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
   a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
@@ -594,13 +618,13 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double bet
   float* kl = nullptr;
   if (beta == 1.0) {
     kl = ctx->colsum;
-    rc = factor_colsum(W, d.C, d.R, d.T, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);     // nmf.py:128-131
+    rc = factor_colsum(W, d.C, d.R, d.w_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);     // nmf.py:128-131
   } else {
     rc = nmfd_dgrad(d, ctx->Pp, W, ctx->den, ctx->dgrad_nsplit, st);
   }
   if (rc) return rc;
   ApplyArgs a{};
-  a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;
+  a.param = H; a.numel = (int64_t)d.B * d.R * d.h_inner(); a.R = d.R; a.inner = d.h_inner(); a.rowlen = (int64_t)d.R * d.h_inner();
   a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->dgrad_nsplit;
   a.chunk_stride = a.numel; a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
   a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;

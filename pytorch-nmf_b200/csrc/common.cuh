@@ -94,16 +94,27 @@ int matrix_minmax(const float* V, int64_t rows, int64_t cols, int64_t ld, float*
 int sum_partials(const double* p, int n, double* out, cudaStream_t st);
 
 // nmfd.cu ----------------------------------------------------------------------------------
-struct NmfdShape { int B, C, L, R, T, Lin; };
+// L, T, Lin are the sizes along the LAST (contiguous) axis; NMF2D / NMF3D (nmf.py:782-942) add up to two outer axes of the
+// target (X1, X2), of the kernel (T1, T2) and of H (X - T + 1).  The outer axes are loops around the same sliding GEMMs.
+struct NmfdShape {
+  int B, C, L, R, T, Lin;
+  int X1 = 1, X2 = 1, T1 = 1, T2 = 1;
+  __host__ __device__ int J1() const { return X1 - T1 + 1; }
+  __host__ __device__ int J2() const { return X2 - T2 + 1; }
+  __host__ __device__ int64_t v_inner() const { return (int64_t)X1 * X2 * L; }        // target elements per (b, c)
+  __host__ __device__ int64_t w_inner() const { return (int64_t)T1 * T2 * T; }        // kernel elements per (c, r)
+  __host__ __device__ int64_t h_inner() const { return (int64_t)J1() * J2() * Lin; }  // activation elements per (b, r)
+  __host__ __device__ bool one_d() const { return X1 == 1 && X2 == 1 && T1 == 1 && T2 == 1; }
+};
 // WH = conv(H, W); writes Pn (and Pp when beta != 1) (B,C,L) or, when loss_blocks != nullptr,
 // reduces beta_div(WH, V) instead.
 int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const float* H, double beta,
                    float* Pn, float* Pp, double* loss_blocks, int max_blocks, double* loss_dev,
                    cudaStream_t st);
 int nmfd_max_blocks(const NmfdShape& s);
-// out[c,r,t] = sum_{b,l} G[b,c,l] H[b,r,l-t]
+// out[c,r,t] = sum_{b,x} G[b,c,x] H[b,r,x-t]   (x, t multi-indices over up to three axes)
 int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, cudaStream_t st);
-// out[split][b,r,j] = sum_{c in split, t} W[c,r,t] G[b,c,j+t]
+// out[split][b,r,j] = sum_{c in split, t} W[c,r,t] G[b,c,j+t]   (j, t multi-indices)
 int nmfd_dgrad(const NmfdShape& s, const float* G, const float* W, float* out, int nsplit, cudaStream_t st);
 int nmfd_dgrad_nsplit(const NmfdShape& s);
 

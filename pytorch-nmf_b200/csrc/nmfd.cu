@@ -4,6 +4,10 @@
 //   wgrad : gW[c,r,t]   = sum_{b,l} G[b,c,l] H[b,r,l-t]          autograd of the above w.r.t. W
 //   dgrad : gH[b,r,j]   = sum_{c,t} W[c,r,t] G[b,c,j+t]          autograd of the above w.r.t. H
 //
+// NMF2D / NMF3D (nmf.py:782-942: conv2d / conv3d with flipped kernels and full padding) are the same three contractions
+// with multi-indices l = (x1, x2, l), t = (t1, t2, t): the LAST axis is the sliding axis of the kernels below, the outer
+// axes are loops (recon, dgrad: over the outer shifts; wgrad: over the outer positions) around the same inner product.
+//
 // No Toeplitz/im2col matrix is ever formed: each CTA stages one contiguous window of the shifted
 // operand in shared memory and every thread slides a 4-element register window across it (one shared
 // load + one float4 load per 16 FMAs).
@@ -47,7 +51,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
   return t;
 }
 
-// grid (ceil(L/64), ceil(C/64), B), 256 threads; thread (ty,tx) owns c = 4ty..4ty+3, l = 4tx..4tx+3.
+// grid (ceil(L/64) * X1 * X2, ceil(C/64), B), 256 threads; thread (ty,tx) owns c = 4ty..4ty+3, l = 4tx..4tx+3.
 template <int MODE, bool LOSS>
 __global__ void __launch_bounds__(256)
 nmfd_recon_kernel(NmfdShape s, const float* __restrict__ V, const float* __restrict__ W,
@@ -57,22 +61,32 @@ nmfd_recon_kernel(NmfdShape s, const float* __restrict__ V, const float* __restr
   __shared__ float Hs[kT + kTK];                         // window of H[b,r,:]
   __shared__ double red[8];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int l0 = blockIdx.x * kT, c0 = blockIdx.y * kT, b = blockIdx.z;
-  const int RT = s.R * s.T;
+  const int ntl = (s.L + kT - 1) / kT;
+  const int outer = blockIdx.x / ntl;                    // (x1, x2): outer position of this tile of the target
+  const int x1 = outer / s.X2, x2 = outer - x1 * s.X2;
+  const int l0 = (blockIdx.x - outer * ntl) * kT, c0 = blockIdx.y * kT, b = blockIdx.z;
+  const int J1 = s.J1(), J2 = s.J2();
+  const int64_t WI = s.w_inner(), RT = (int64_t)s.R * WI;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int r = 0; r < s.R; ++r) {
-    const float* Hrow = H + ((int64_t)b * s.R + r) * s.Lin;
+  const int nouter = s.T1 * s.T2;
+  for (int ro = 0; ro < s.R * nouter; ++ro) {
+    const int r = ro / nouter, to = ro - r * nouter;
+    const int t1 = to / s.T2, t2 = to - t1 * s.T2;
+    const int j1 = x1 - t1, j2 = x2 - t2;              // outer position in H (block-uniform)
+    if (j1 < 0 || j1 >= J1 || j2 < 0 || j2 >= J2) continue;
+    const float* Hrow = H + ((((int64_t)b * s.R + r) * J1 + j1) * J2 + j2) * s.Lin;
+    const int64_t wofs = (int64_t)r * WI + (int64_t)to * s.T;
     for (int t0 = 0; t0 < s.T; t0 += kTK) {
       __syncthreads();
       for (int idx = tid; idx < kT * kTK; idx += 256) {
         int c = idx / kTK, tt = idx - c * kTK;
         float w = 0.f;
-        if (c0 + c < s.C && t0 + tt < s.T) w = W[(int64_t)(c0 + c) * RT + r * s.T + t0 + tt];
+        if (c0 + c < s.C && t0 + tt < s.T) w = W[(int64_t)(c0 + c) * RT + wofs + t0 + tt];
         Ws[tt * kLd + c] = w;
       }
       for (int i = tid; i < kT + kTK - 1; i += 256) {
@@ -108,7 +122,7 @@ nmfd_recon_kernel(NmfdShape s, const float* __restrict__ V, const float* __restr
     for (int j = 0; j < 4; ++j) {
       int l = l0 + 4 * tx + j;
       if (c < s.C && l < s.L) {
-        int64_t off = ((int64_t)b * s.C + c) * s.L + l;
+        int64_t off = ((((int64_t)b * s.C + c) * s.X1 + x1) * s.X2 + x2) * s.L + l;
         float v = V[off];
         if (LOSS) {
           local += loss_term_d<MODE>(v, acc[i][j], beta);
@@ -128,29 +142,38 @@ nmfd_recon_kernel(NmfdShape s, const float* __restrict__ V, const float* __restr
   }
 }
 
-// grid (ceil(T/64), ceil(C/64), R); thread (ty,tx): c = 4ty.., t = 4tx..
+// grid (ceil(T/64) * R * T1 * T2, ceil(C/64)); thread (ty,tx): c = 4ty.., t = 4tx..
 __global__ void __launch_bounds__(256)
 nmfd_wgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restrict__ H,
                   float* __restrict__ out) {
   __shared__ __align__(16) float Gs[kTK * kLd];          // Gs[ll][c]
   __shared__ float Hs[kT + kTK];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int t0 = blockIdx.x * kT, c0 = blockIdx.y * kT, r = blockIdx.z;
+  const int ntt = (s.T + kT - 1) / kT;
+  const int zo = blockIdx.x / ntt;                        // (r, t1, t2)
+  const int nouter = s.T1 * s.T2;
+  const int r = zo / nouter, to = zo - r * nouter;
+  const int t1 = to / s.T2, t2 = to - t1 * s.T2;
+  const int t0 = (blockIdx.x - zo * ntt) * kT, c0 = blockIdx.y * kT;
+  const int J1 = s.J1(), J2 = s.J2();
+  const int64_t VI = s.v_inner();
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int b = 0; b < s.B; ++b) {
-    const float* Hrow = H + ((int64_t)b * s.R + r) * s.Lin;
-    const float* Gb = G + (int64_t)b * s.C * s.L;
+  for (int bo = 0; bo < s.B * J1 * J2; ++bo) {            // every H line (b, j1, j2) meets the G line (b, j1 + t1, j2 + t2)
+    const int b = bo / (J1 * J2), jo = bo - b * (J1 * J2);
+    const int j1 = jo / J2, j2 = jo - j1 * J2;
+    const float* Hrow = H + ((((int64_t)b * s.R + r) * J1 + j1) * J2 + j2) * s.Lin;
+    const float* Gb = G + (int64_t)b * s.C * VI + ((int64_t)(j1 + t1) * s.X2 + (j2 + t2)) * s.L;
     for (int l0 = 0; l0 < s.L; l0 += kTK) {
       __syncthreads();
       for (int idx = tid; idx < kT * kTK; idx += 256) {
         int c = idx / kTK, ll = idx - c * kTK;
         float g = 0.f;
-        if (c0 + c < s.C && l0 + ll < s.L) g = Gb[(int64_t)(c0 + c) * s.L + l0 + ll];
+        if (c0 + c < s.C && l0 + ll < s.L) g = Gb[(int64_t)(c0 + c) * VI + l0 + ll];
         Gs[ll * kLd + c] = g;
       }
       for (int i = tid; i < kT + kTK - 1; i += 256) {
@@ -181,12 +204,12 @@ nmfd_wgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int t = t0 + 4 * tx + j;
-      if (c < s.C && t < s.T) out[((int64_t)c * s.R + r) * s.T + t] = acc[i][j];
+      if (c < s.C && t < s.T) out[(((int64_t)c * s.R + r) * nouter + to) * s.T + t] = acc[i][j];
     }
   }
 }
 
-// grid (ceil(Lin/JTILE), nsplit, B); block = RG x JT threads (RG*JT = 256); thread: r = 4rg.., j = 4jx..
+// grid (ceil(Lin/JTILE) * J1 * J2, nsplit, B); block = RG x JT threads (RG*JT = 256); thread: r = 4rg.., j = 4jx..
 template <int RG>
 __global__ void __launch_bounds__(256)
 nmfd_dgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restrict__ W,
@@ -198,25 +221,32 @@ nmfd_dgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restr
   __shared__ float Gs[JTILE + kTK];
   const int tid = threadIdx.x;
   const int rg = tid % RG, jx = tid / RG;
-  const int j0 = blockIdx.x * JTILE, split = blockIdx.y, b = blockIdx.z;
+  const int ntj = (s.Lin + JTILE - 1) / JTILE;
+  const int outer = blockIdx.x / ntj;                    // (j1, j2): outer position of this tile of H
+  const int J2 = s.J2();
+  const int j1 = outer / J2, j2 = outer - j1 * J2;
+  const int j0 = (blockIdx.x - outer * ntj) * JTILE, split = blockIdx.y, b = blockIdx.z;
   const int cps = (s.C + nsplit - 1) / nsplit;
   const int cbeg = split * cps, cend = min(s.C, cbeg + cps);
-  const int RT = s.R * s.T;
+  const int64_t WI = s.w_inner(), RT = (int64_t)s.R * WI, VI = s.v_inner();
+  const int nouter = s.T1 * s.T2;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int c = cbeg; c < cend; ++c) {
-    const float* Grow = G + ((int64_t)b * s.C + c) * s.L;
-    const float* Wc = W + (int64_t)c * RT;
+  for (int co = cbeg * nouter; co < cend * nouter; ++co) {
+    const int c = co / nouter, to = co - c * nouter;
+    const int t1 = to / s.T2, t2 = to - t1 * s.T2;
+    const float* Grow = G + ((int64_t)b * s.C + c) * VI + ((int64_t)(j1 + t1) * s.X2 + (j2 + t2)) * s.L;
+    const float* Wc = W + (int64_t)c * RT + (int64_t)to * s.T;
     for (int t0 = 0; t0 < s.T; t0 += kTK) {
       __syncthreads();
       for (int idx = tid; idx < kTK * Rp; idx += 256) {
         int r = idx / kTK, tt = idx - r * kTK;
         float w = 0.f;
-        if (r < s.R && t0 + tt < s.T) w = Wc[r * s.T + t0 + tt];
+        if (r < s.R && t0 + tt < s.T) w = Wc[(int64_t)r * WI + t0 + tt];
         Ws[tt * Rp + r] = w;
       }
       for (int i = tid; i < JTILE + kTK - 1; i += 256) {
@@ -241,14 +271,15 @@ nmfd_dgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restr
       }
     }
   }
-  float* o = out + (int64_t)split * s.B * s.R * s.Lin;
+  const int64_t HI = s.h_inner();
+  float* o = out + (int64_t)split * s.B * s.R * HI;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int r = 4 * rg + i;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int jj = j0 + 4 * jx + j;
-      if (r < s.R && jj < s.Lin) o[((int64_t)b * s.R + r) * s.Lin + jj] = acc[i][j];
+      if (r < s.R && jj < s.Lin) o[((int64_t)b * s.R + r) * HI + (int64_t)outer * s.Lin + jj] = acc[i][j];
     }
   }
 }
@@ -262,12 +293,12 @@ int dgrad_rg(int R) {
 }  // namespace
 
 int nmfd_max_blocks(const NmfdShape& s) {
-  return (int)(ceil_div(s.L, kT) * ceil_div(s.C, kT) * s.B);
+  return (int)(ceil_div(s.L, kT) * s.X1 * s.X2 * ceil_div(s.C, kT) * s.B);
 }
 
 int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const float* H, double beta, float* Pn,
                    float* Pp, double* loss_blocks, int max_blocks, double* loss_dev, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(s.L, kT), (unsigned)ceil_div(s.C, kT), (unsigned)s.B);
+  dim3 grid((unsigned)(ceil_div(s.L, kT) * s.X1 * s.X2), (unsigned)ceil_div(s.C, kT), (unsigned)s.B);
   const int nblocks = (int)(grid.x * grid.y * grid.z);
   const bool loss = loss_blocks != nullptr;
   if (loss && nblocks > max_blocks) { set_error("nmfd loss: partial buffer too small"); return 1; }
@@ -288,7 +319,7 @@ int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const flo
 }
 
 int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(s.T, kT), (unsigned)ceil_div(s.C, kT), (unsigned)s.R);
+  dim3 grid((unsigned)(ceil_div(s.T, kT) * s.R * s.T1 * s.T2), (unsigned)ceil_div(s.C, kT), 1);
   nmfd_wgrad_kernel<<<grid, 256, 0, st>>>(s, G, H, out);
   NMF_LAUNCH_CHECK();
   return 0;
@@ -297,7 +328,7 @@ int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, c
 int nmfd_dgrad_nsplit(const NmfdShape& s) {
   const int rg = dgrad_rg(s.R);
   const int jtile = 4 * (256 / rg);
-  int64_t tiles = ceil_div(s.Lin, jtile) * s.B;
+  int64_t tiles = ceil_div(s.Lin, jtile) * s.J1() * s.J2() * s.B;
   int64_t ns = ceil_div(148 * 4, tiles);
   if (ns > s.C) ns = s.C;
   if (ns > 64) ns = 64;
@@ -309,7 +340,7 @@ int nmfd_dgrad(const NmfdShape& s, const float* G, const float* W, float* out, i
   if (s.R > 256) { set_error("nmfd_dgrad: rank must be <= 256"); return 1; }
   const int rg = dgrad_rg(s.R);
   const int jtile = 4 * (256 / rg);
-  dim3 grid((unsigned)ceil_div(s.Lin, jtile), (unsigned)nsplit, (unsigned)s.B);
+  dim3 grid((unsigned)(ceil_div(s.Lin, jtile) * s.J1() * s.J2()), (unsigned)nsplit, (unsigned)s.B);
   switch (rg) {
     case 1: nmfd_dgrad_kernel<1><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
     case 2: nmfd_dgrad_kernel<2><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;

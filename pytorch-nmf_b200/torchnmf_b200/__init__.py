@@ -3,7 +3,7 @@ torchnmf.nmf.NMF / NMFD module surface.  See DESIGN.md / INTEGRATION.md at the r
 __version__ = "0.1.0"
 
 from . import constants, metrics, nmf, plca, trainer  # noqa: F401
-from .nmf import NMF, NMFD, BaseComponent  # noqa: F401
+from .nmf import NMF, NMFD, NMF2D, NMF3D, BaseComponent  # noqa: F401
 from .plca import PLCA  # noqa: F401
 from .trainer import BetaMu  # noqa: F401
 from .engine import release_workspaces  # noqa: F401

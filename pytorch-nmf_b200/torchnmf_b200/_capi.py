@@ -43,6 +43,7 @@ SIGNATURES = {
     "nmfb200_nmf_w_apply": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmf_contract_only": (_int, [_vp, _vp, _vp, _int, _dbl, _vp]),
     "nmfb200_nmfd_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _i64, _i64, _int]),
+    "nmfb200_nmfnd_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _int, _c.POINTER(_i64), _i64, _c.POINTER(_i64), _int]),
     "nmfb200_nmfd_set_target": (_int, [_vp, _vp, _vp]),
     "nmfb200_nmfd_update_w": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmfd_update_h": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),

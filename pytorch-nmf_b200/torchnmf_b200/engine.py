@@ -184,7 +184,7 @@ class CudaNmfEngine(_CudaEngine):
 
 
 class CudaNmfdEngine(_CudaEngine):
-    """NMFD on one GPU: V (B,C,L), W (C,R,T), H (B,R,L-T+1)."""
+    """NMFD / NMF2D / NMF3D on one GPU: V (B,C,*X), W (C,R,*K), H (B,R,*(X-K+1)) over one to three convolved axes."""
     kind = "nmfd"
 
     def __init__(self, V, W, H, precision="auto"):
@@ -192,14 +192,23 @@ class CudaNmfdEngine(_CudaEngine):
         self.device = W.device
         for t, n in ((V, "V"), (W, "W"), (H, "H")):
             _check_f32_cuda(t, n, self.device)
-        B, C, L = V.shape
-        _, R, T = W.shape
-        assert W.shape == (C, R, T) and H.shape == (B, R, L - T + 1)
+        B, C, *X = V.shape
+        _, R, *K = W.shape
+        nd = len(X)
+        assert 1 <= nd <= 3 and len(K) == nd
+        assert W.shape == (C, R, *K) and H.shape == (B, R, *(x - k + 1 for x, k in zip(X, K)))
         self.V, self.W, self.H = V, W, H
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self._acquire(("nmfd", dev_index, B, C, L, R, T, precision),
-                      lambda ref: self._lib.nmfb200_nmfd_create(ref, dev_index, B, C, L, R, T,
-                                                                _capi.PRECISIONS[precision]))
+        if nd == 1:
+            create = lambda ref: self._lib.nmfb200_nmfd_create(ref, dev_index, B, C, X[0], R, K[0],
+                                                               _capi.PRECISIONS[precision])
+        else:
+            if precision not in ("auto", "f32"):
+                raise ValueError("NMF2D / NMF3D run on the fp32 kernels: precision must be 'auto' or 'f32'")
+            vd, kd = (ctypes.c_int64 * nd)(*X), (ctypes.c_int64 * nd)(*K)
+            create = lambda ref: self._lib.nmfb200_nmfnd_create(ref, dev_index, B, C, nd, vd, R, kd,
+                                                                _capi.PRECISIONS[precision])
+        self._acquire(("nmfd", dev_index, B, C, tuple(X), R, tuple(K), precision), create)
         self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         _capi.check(self._lib.nmfb200_nmfd_set_target(self._ctx, _ptr(V), _stream(self.device)))
 

@@ -12,8 +12,9 @@ There is no CPU compute path: `fit` on CPU-resident modules copies V / W / H to 
 device, runs there, and copies the factors back into the same Parameter storages ("host buffer"
 mode, the `e2e` number of bench.py).  Without a CUDA device or without the built library it raises.
 
-Sparse targets are accepted and densified on the device (no SDDMM kernel).  Out of scope:
-`sparse_fit`, NMF2D/NMF3D.  `trainer.BetaMu` and `plca.PLCA` live in their own modules.
+`NMF2D` (:782-865) and `NMF3D` (:868-942) run the NMFD contractions with the last axis sliding and the outer axes as loops.
+Sparse targets are accepted by `NMF` and densified on the device (no SDDMM kernel).  Out of scope:
+`sparse_fit`.  `trainer.BetaMu` and `plca.PLCA` live in their own modules.
 """
 import math
 import weakref
@@ -32,7 +33,7 @@ try:
 except Exception:  # pragma: no cover
     _tqdm = None
 
-__all__ = ["BaseComponent", "NMF", "NMFD"]
+__all__ = ["BaseComponent", "NMF", "NMFD", "NMF2D", "NMF3D"]
 
 
 def _gamma(beta):
@@ -129,6 +130,7 @@ class BaseComponent(torch.nn.Module):
     # test hook (tests/oracle_engine.py): an engine class used instead of the CUDA engines, so the host logic of `fit`
     # can be tested on a GPU-less box.  Deliberately NOT a parameter of `fit`: its signature stays the reference's.
     _engine_factory = None
+    _sparse_targets = False       # NMF only (nmf.py:603-638); the convolutive models raise, as in the reference
 
     @torch.no_grad()
     def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
@@ -148,6 +150,8 @@ class BaseComponent(torch.nn.Module):
         is written back into the same Parameter storages in their own dtype.
         """
         sparse_target = V.is_sparse
+        if sparse_target and not self._sparse_targets:
+            raise NotImplementedError                      # nmf.py:294-295: only NMF derives the sparse update
         if sparse_target:
             # The reference's sparse derivation (nmf.py:95-119, :603-638: SDDMM at the non-zeros) is the same update as the
             # dense one on V.to_dense() -- its own tests/test_nmf_sparse.py:8-37 asserts exactly that.  There is no SDDMM
@@ -246,6 +250,7 @@ class BaseComponent(torch.nn.Module):
 class NMF(BaseComponent):
     """Non-negative matrix factorisation  V (N,C) ~= H (N,R) @ W (C,R)^T   (reference: nmf.py:641-697)."""
     _engine_cls = _engine.CudaNmfEngine
+    _sparse_targets = True
 
     def __init__(self, Vshape=None, rank=None, **kwargs):
         if isinstance(Vshape, _Iterable):
@@ -292,3 +297,69 @@ class NMFD(BaseComponent):
         if not ok:
             raise RuntimeError(f"target shape {tuple(V.shape)} does not match H {tuple(self.H.shape)} / "
                                f"W {tuple(self.W.shape)}")
+
+
+def _ntuple(x, n):
+    """torch.nn.modules.utils._pair / _triple: an int repeats, an iterable is taken as is."""
+    return tuple(x) if isinstance(x, _Iterable) else (x,) * n
+
+
+class _NMFnD(BaseComponent):
+    """Shared part of NMF2D / NMF3D: V (B,C,*X) ~= sum over the kernel offsets t of W[:,:,t] @ shift_t(H),
+    W (C,R,*kernel_size), H (B,R,*(X - kernel_size + 1)).  `fit` runs the same three sliding contractions as NMFD with the
+    last axis sliding and the outer axes as loops (csrc/nmfd.cu), in fp32, for every beta."""
+    _engine_cls = _engine.CudaNmfdEngine
+    _nd = 0
+
+    def _check_target_shape(self, V):
+        nd = self._nd
+        ok = (V.dim() == nd + 2 and V.shape[0] == self.H.shape[0] and V.shape[1] == self.W.shape[0]
+              and all(V.shape[2 + i] == self.H.shape[2 + i] + self.W.shape[2 + i] - 1 for i in range(nd)))
+        if not ok:
+            raise RuntimeError(f"target shape {tuple(V.shape)} does not match H {tuple(self.H.shape)} / "
+                               f"W {tuple(self.W.shape)}")
+
+
+class NMF2D(_NMFnD):
+    """Non-negative matrix factor 2-D deconvolution (reference: nmf.py:782-865).
+
+    V (B,C,L,M) ~= conv2d(H, flipped W, full padding),  W (C,R,k0,k1),  H (B,R,L-k0+1,M-k1+1).
+    """
+    _nd = 2
+
+    def __init__(self, Vshape=None, rank=None, kernel_size=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            kernel_size = _ntuple(kernel_size, 2)
+            kh, kw = kernel_size
+            batch, channel, K, M = Vshape                  # wrong arity raises, as in the reference (:852)
+            rank = rank if rank else K
+            kwargs["W"] = (channel, rank) + kernel_size
+            kwargs["H"] = (batch, rank, K - kh + 1, M - kw + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W):
+        return F.conv2d(H, W.flip((2, 3)), padding=(W.shape[2] - 1, W.shape[3] - 1))          # nmf.py:861-865
+
+
+class NMF3D(_NMFnD):
+    """Non-negative matrix factor 3-D deconvolution (reference: nmf.py:868-942).
+
+    V (B,C,N,K,M) ~= conv3d(H, flipped W, full padding),  W (C,R,k0,k1,k2),  H (B,R,N-k0+1,K-k1+1,M-k2+1).
+    """
+    _nd = 3
+
+    def __init__(self, Vshape=None, rank=None, kernel_size=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            kernel_size = _ntuple(kernel_size, 3)
+            kd, kh, kw = kernel_size
+            batch, channel, N, K, M = Vshape               # wrong arity raises, as in the reference (:928)
+            rank = rank if rank else K
+            kwargs["W"] = (channel, rank) + kernel_size
+            kwargs["H"] = (batch, rank, N - kd + 1, K - kh + 1, M - kw + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W):
+        pad = (W.shape[2] - 1, W.shape[3] - 1, W.shape[4] - 1)
+        return F.conv3d(H, W.flip((2, 3, 4)), padding=pad)                                     # nmf.py:938-942

@@ -168,3 +168,46 @@ def test_fit_signature_is_the_references():
     assert list(sig.parameters)[:8] == ["self", "V", "beta", "tol", "max_iter", "verbose", "alpha", "l1_ratio"]   # nmf.py:298-306
     extras = [p for p in sig.parameters.values() if p.kind is inspect.Parameter.KEYWORD_ONLY]
     assert sorted(p.name for p in extras) == ["group", "precision"]
+
+
+# ---- NMF2D / NMF3D constructors: reference tests/test_nmf.py:72-101 and the docstring examples nmf.py:830-841, :912-923 ----
+def test_nmf2d_valid_construct():
+    from torchnmf_b200 import NMF2D
+    m = NMF2D((2, 5, 30, 20), 4)
+    assert m().shape == (2, 5, 30, 20)
+    m = NMF2D((1, 1, 33, 50), 16, 3)
+    assert m.W.shape == (1, 16, 3, 3) and m.H.shape == (1, 16, 31, 48) and m().shape == (1, 1, 33, 50)
+    m = NMF2D((1, 2, 12, 9), 3, (2, 4))
+    assert m.W.shape == (2, 3, 2, 4) and m.H.shape == (1, 3, 11, 6)
+
+
+@pytest.mark.parametrize("Vshape", [(100, 50), (100,), (100, 50) * 6])
+def test_nmf2d_invalid_construct(Vshape):
+    from torchnmf_b200 import NMF2D
+    with pytest.raises(Exception):
+        NMF2D(Vshape)
+
+
+def test_nmf3d_valid_construct():
+    from torchnmf_b200 import NMF3D
+    m = NMF3D((1, 3, 16, 16, 20), 8, (5, 5, 6))
+    assert m.W.shape == (3, 8, 5, 5, 6) and m.H.shape == (1, 8, 12, 12, 15) and m().shape == (1, 3, 16, 16, 20)
+    assert NMF3D((2, 4, 6, 7, 8), 2)().shape == (2, 4, 6, 7, 8)
+
+
+@pytest.mark.parametrize("Vshape", [(100, 50), (100,), (100, 50) * 4])
+def test_nmf3d_invalid_construct(Vshape):
+    from torchnmf_b200 import NMF3D
+    with pytest.raises(Exception):
+        NMF3D(Vshape)
+
+
+def test_convolutive_models_refuse_sparse_targets_like_the_reference():
+    """nmf.py:294-295: only NMF derives the sparse update; NMFD / NMF2D / NMF3D raise NotImplementedError."""
+    from torchnmf_b200 import NMFD, NMF2D
+    V = torch.rand(1, 4, 12).to_sparse()
+    with pytest.raises(NotImplementedError):
+        NMFD(V.shape, 2, 3).fit(V)
+    V = torch.rand(1, 2, 6, 7).to_sparse()
+    with pytest.raises(NotImplementedError):
+        NMF2D(V.shape, 2, 2).fit(V)

@@ -133,3 +133,33 @@ def test_oracle_matches_reference_round2_fixtures(name):
     # 50 iterations, multi-threaded BLAS on both sides: reduction order differs -> 2e-4
     assert torch.allclose(W[::ws], torch.from_numpy(c["W_sub"]), rtol=2e-4, atol=1e-6 * float(c["w_absmax"]))
     assert torch.allclose(Hs, torch.from_numpy(c["H_sub"]), rtol=2e-4, atol=1e-6 * float(c["h_absmax"]))
+
+
+ND_CASES = load_golden("reference_nd.npz")
+
+
+@pytest.mark.parametrize("name", sorted(ND_CASES))
+def test_oracle_matches_reference_nmf2d_nmf3d(name):
+    """NMF2D / NMF3D (nmf.py:782-942): the shifted-product restatement against fits of the real reference."""
+    c = ND_CASES[name]
+    torch.set_num_threads(1)
+    W, H, n_iter, losses = orc.fit(
+        c["V"], c["W0"], c["H0"], beta=c["beta"], tol=c["tol"], max_iter=c["max_iter"],
+        alpha=c["alpha"], l1_ratio=c["l1_ratio"],
+        trainable_W=bool(c.get("trainable_W", 1)), trainable_H=bool(c.get("trainable_H", 1)), kind=c["kind"])
+    assert n_iter == c["n_iter"]
+    assert torch.allclose(W, c["W"], rtol=1e-4, atol=1e-7), (W - c["W"]).abs().max()
+    assert torch.allclose(H, c["H"], rtol=1e-4, atol=1e-7), (H - c["H"]).abs().max()
+    assert len(losses) == len(c["losses"])
+    for a, b in zip(losses, c["losses"]):
+        assert math.isclose(a, b, rel_tol=1e-4, abs_tol=1e-6)
+
+
+def test_nmfnd_reconstruct_is_the_full_convolution():
+    """The shifted-product form equals conv2d / conv3d with the flipped kernel and full padding (nmf.py:861-865, :938-942)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    H, W = torch.rand(2, 3, 6, 7), torch.rand(4, 3, 2, 3)
+    assert torch.allclose(orc.nmfnd_reconstruct(H, W), F.conv2d(H, W.flip((2, 3)), padding=(1, 2)), atol=1e-5)
+    H, W = torch.rand(1, 2, 4, 5, 6), torch.rand(3, 2, 2, 2, 3)
+    assert torch.allclose(orc.nmfnd_reconstruct(H, W), F.conv3d(H, W.flip((2, 3, 4)), padding=(1, 1, 2)), atol=1e-5)
