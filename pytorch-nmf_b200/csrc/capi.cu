@@ -43,6 +43,7 @@ struct nmfb200_ctx {
   // NMFD
   float* Pn = nullptr;
   float* Pp = nullptr;
+  int wgrad_nsplit = 1;
   int dgrad_nsplit = 1;
   // tensor-core path state (tc_nmf.cu / tc_nmfd.cu)
   TcState* tc = nullptr;
@@ -461,7 +462,8 @@ static int nmfd_create_impl(nmfb200_ctx** out, int device, int64_t B, int64_t C,
   c->d = NmfdShape{(int)B, (int)C, (int)L, (int)R, (int)T, (int)(L - T + 1)};
   c->d.X1 = (int)X[0]; c->d.X2 = (int)X[1]; c->d.T1 = (int)K[0]; c->d.T2 = (int)K[1];
   c->dgrad_nsplit = nmfd_dgrad_nsplit(c->d);
-  int64_t pf = C * R * c->d.w_inner();
+  c->wgrad_nsplit = nmfd_wgrad_nsplit(c->d);
+  int64_t pf = (int64_t)c->wgrad_nsplit * C * R * c->d.w_inner();
   int64_t hf = (int64_t)c->dgrad_nsplit * B * R * c->d.h_inner();
   if (hf > pf) pf = hf;
   c->part_floats = pf;
@@ -570,19 +572,19 @@ int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double bet
   if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);            // this update bypasses the tensor-core state
   int rc = nmfd_phi(ctx, W, H, beta, st);
   if (rc) return rc;
-  rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, st);
+  rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, ctx->wgrad_nsplit, st);
   if (rc) return rc;
   float* kl = nullptr;
   if (beta == 1.0) {
     kl = ctx->colsum + d.R;
     rc = factor_colsum(H, d.B, d.R, d.h_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);   // nmf.py:122-125
   } else {
-    rc = nmfd_wgrad(d, ctx->Pp, H, ctx->den, st);
+    rc = nmfd_wgrad(d, ctx->Pp, H, ctx->den, ctx->wgrad_nsplit, st);
   }
   if (rc) return rc;
   ApplyArgs a{};
   a.param = W; a.numel = (int64_t)d.C * d.R * d.w_inner(); a.R = d.R; a.inner = d.w_inner(); a.rowlen = (int64_t)d.R * d.w_inner();
-  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = 1; a.chunk_stride = 0;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->wgrad_nsplit; a.chunk_stride = a.numel;
   a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
   a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
   return apply_update(a, st);

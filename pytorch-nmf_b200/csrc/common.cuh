@@ -113,7 +113,8 @@ int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const flo
                    cudaStream_t st);
 int nmfd_max_blocks(const NmfdShape& s);
 // out[c,r,t] = sum_{b,x} G[b,c,x] H[b,r,x-t]   (x, t multi-indices over up to three axes)
-int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, cudaStream_t st);
+int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, int nsplit, cudaStream_t st);   // out[split][C,R,T]
+int nmfd_wgrad_nsplit(const NmfdShape& s);
 // out[split][b,r,j] = sum_{c in split, t} W[c,r,t] G[b,c,j+t]   (j, t multi-indices)
 int nmfd_dgrad(const NmfdShape& s, const float* G, const float* W, float* out, int nsplit, cudaStream_t st);
 int nmfd_dgrad_nsplit(const NmfdShape& s);

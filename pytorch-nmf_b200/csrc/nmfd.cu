@@ -1,24 +1,28 @@
-// NMFD (1-D convolutive NMF) contractions as im2col-free sliding GEMMs on CUDA cores, fp32.
+// NMFD / NMF2D / NMF3D (convolutive NMF over one to three axes) contractions as im2col-free sliding GEMMs on CUDA cores, fp32.
 //
-//   recon : WH[b,c,l]   = sum_{r,t} W[c,r,t] H[b,r,l-t]          nmf.py:776-779 (conv1d, flipped kernel, full pad)
-//   wgrad : gW[c,r,t]   = sum_{b,l} G[b,c,l] H[b,r,l-t]          autograd of the above w.r.t. W
+//   recon : WH[b,c,x]   = sum_{r,t} W[c,r,t] H[b,r,x-t]          nmf.py:776-779, :861-865, :938-942 (flipped kernel, full pad)
+//   wgrad : gW[c,r,t]   = sum_{b,x} G[b,c,x] H[b,r,x-t]          autograd of the above w.r.t. W
 //   dgrad : gH[b,r,j]   = sum_{c,t} W[c,r,t] G[b,c,j+t]          autograd of the above w.r.t. H
 //
-// NMF2D / NMF3D (nmf.py:782-942: conv2d / conv3d with flipped kernels and full padding) are the same three contractions
-// with multi-indices l = (x1, x2, l), t = (t1, t2, t): the LAST axis is the sliding axis of the kernels below, the outer
-// axes are loops (recon, dgrad: over the outer shifts; wgrad: over the outer positions) around the same inner product.
+// x, t, j are multi-indices over the convolved axes.  The LAST axis is the sliding axis of the kernels; the outer axes
+// (NmfdShape::X1, X2 / T1, T2) are loops: recon and dgrad loop over the outer kernel offsets, wgrad over the outer positions
+// ("lines").  No Toeplitz/im2col matrix is ever formed: each CTA stages contiguous windows of the shifted operand in shared
+// memory and every thread slides a 4-element register window across its line (one shared load + one float4 load per 16
+// FMAs).
 //
-// No Toeplitz/im2col matrix is ever formed: each CTA stages one contiguous window of the shifted
-// operand in shared memory and every thread slides a 4-element register window across it (one shared
-// load + one float4 load per 16 FMAs).
+// Tile shapes follow the problem.  A thread owns 4 rows x 4 columns of the output tile; the row tile MT (channels for recon
+// and wgrad, components for dgrad) is 4 ... 64, and the 256 / (MT / 4) thread columns that remain cover
+//   recon / dgrad: 64 positions of the sliding axis on each of 64 / MT consecutive outer lines,
+//   wgrad        : the offsets t of several components r -- and, when those do not fill the block, of several outer kernel
+//                  offsets (t1, t2) -- at once,
+// so a 3-channel target or a 16-tap kernel does not leave most of the block idle.
 #include "common.cuh"
 
 namespace nmfb200 {
 
 namespace {
 
-constexpr int kT = 64;     // output tile edge
-constexpr int kLd = 68;    // shared pitch
+constexpr int kLT = 64;    // positions of the sliding axis per line tile
 constexpr int kTK = 32;    // k-chunk (shifts or samples) per stage
 
 template <int MODE>
@@ -51,110 +55,194 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
   return t;
 }
 
-// grid (ceil(L/64) * X1 * X2, ceil(C/64), B), 256 threads; thread (ty,tx) owns c = 4ty..4ty+3, l = 4tx..4tx+3.
-template <int MODE, bool LOSS>
+template <int MT>
+struct Geo {
+  static constexpr int TY = MT / 4;          // thread rows (4 output rows each)
+  static constexpr int TX = 256 / TY;        // thread columns (4 output columns each)
+  static constexpr int XT = TX / 16;         // outer lines per block (recon / dgrad): 16 thread columns = 64 positions a line
+  static constexpr int NCOL = 4 * TX;        // output columns per block (wgrad)
+  static constexpr int PAD = MT + 4;         // shared pitch of the row-tile operand
+  static constexpr int NTO = MT <= 16 ? 8 : 1;               // wgrad: outer kernel offsets a block may cover
+  static constexpr int HS = (NCOL / 4) * (4 + kTK);          // wgrad: floats of H windows (worst case: 4 offsets per component)
+};
+
+// ---- recon (FWD) and dgrad (!FWD): out[m, pos] = sum_{k, t} A[m, k, t] X[k, pos -/+ t] ---------------------------------------
+//   FWD : m = c, k = r, X = H, shift -t, zero outside H; the epilogue applies phi against V (or reduces the loss)
+//   !FWD: m = r, k = c in this block's split, X = G, shift +t; the epilogue writes the partial sums of this split
+// grid (line tiles * line groups, row tiles * nsplit, B), 256 threads
+struct SlideArgs {
+  const float* A;            // W
+  const float* X;            // H (FWD) or G
+  int M, K;                  // rows of the output, size of the reduced dimension
+  int64_t sm, sk;            // strides of A over m and k (elements); the offset (t1, t2, t) is contiguous
+  int nsplit;                // !FWD: splits of k
+  const float* V; float beta; float* Pn; float* Pp; double* block_partials;     // FWD epilogue
+  float* out;                // !FWD: [split][B][R][h_inner]
+};
+
+template <int MT, bool FWD, int MODE, bool LOSS>
 __global__ void __launch_bounds__(256)
-nmfd_recon_kernel(NmfdShape s, const float* __restrict__ V, const float* __restrict__ W,
-                  const float* __restrict__ H, float beta, float* __restrict__ Pn, float* __restrict__ Pp,
-                  double* __restrict__ block_partials) {
-  __shared__ __align__(16) float Ws[kTK * kLd];          // Ws[tt][c]
-  __shared__ float Hs[kT + kTK];                         // window of H[b,r,:]
+nmfd_slide_kernel(NmfdShape s, SlideArgs a) {
+  using G = Geo<MT>;
+  constexpr int WIN = kLT + kTK;                          // window pitch per line (kLT + kTK - 1 elements used)
+  __shared__ __align__(16) float As[kTK * G::PAD];        // As[tt][m]
+  __shared__ float Xs[G::XT * WIN];
   __shared__ double red[8];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int ntl = (s.L + kT - 1) / kT;
-  const int outer = blockIdx.x / ntl;                    // (x1, x2): outer position of this tile of the target
-  const int x1 = outer / s.X2, x2 = outer - x1 * s.X2;
-  const int l0 = (blockIdx.x - outer * ntl) * kT, c0 = blockIdx.y * kT, b = blockIdx.z;
+  const int tid = threadIdx.x, tx = tid % G::TX, ty = tid / G::TX;
+  const int lt = tx & 15, xl = tx >> 4;
+  const int OUT = FWD ? s.X1 * s.X2 : s.J1() * s.J2();    // outer lines of the output
+  const int O2 = FWD ? s.X2 : s.J2();
+  const int LOUT = FWD ? s.L : s.Lin;                     // output length along the sliding axis
+  const int nlt = (LOUT + kLT - 1) / kLT;
+  const int lg = blockIdx.x / nlt;
+  const int l0 = (blockIdx.x - lg * nlt) * kLT;
+  const int mtiles = (a.M + MT - 1) / MT;
+  const int split = blockIdx.y / mtiles;
+  const int m0 = (blockIdx.y - split * mtiles) * MT;
+  const int b = blockIdx.z;
+  const int kps = (a.K + a.nsplit - 1) / a.nsplit;
+  const int kbeg = split * kps, kend = min(a.K, kbeg + kps);
   const int J1 = s.J1(), J2 = s.J2();
-  const int64_t WI = s.w_inner(), RT = (int64_t)s.R * WI;
+  const int nouter = s.T1 * s.T2;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int nouter = s.T1 * s.T2;
-  for (int ro = 0; ro < s.R * nouter; ++ro) {
-    const int r = ro / nouter, to = ro - r * nouter;
+  for (int ko = kbeg * nouter; ko < kend * nouter; ++ko) {
+    const int k = ko / nouter, to = ko - k * nouter;
     const int t1 = to / s.T2, t2 = to - t1 * s.T2;
-    const int j1 = x1 - t1, j2 = x2 - t2;              // outer position in H (block-uniform)
-    if (j1 < 0 || j1 >= J1 || j2 < 0 || j2 >= J2) continue;
-    const float* Hrow = H + ((((int64_t)b * s.R + r) * J1 + j1) * J2 + j2) * s.Lin;
-    const int64_t wofs = (int64_t)r * WI + (int64_t)to * s.T;
     for (int t0 = 0; t0 < s.T; t0 += kTK) {
       __syncthreads();
-      for (int idx = tid; idx < kT * kTK; idx += 256) {
-        int c = idx / kTK, tt = idx - c * kTK;
+      for (int idx = tid; idx < MT * kTK; idx += 256) {
+        const int m = idx / kTK, tt = idx - m * kTK;
         float w = 0.f;
-        if (c0 + c < s.C && t0 + tt < s.T) w = W[(int64_t)(c0 + c) * RT + wofs + t0 + tt];
-        Ws[tt * kLd + c] = w;
+        if (m0 + m < a.M && t0 + tt < s.T) w = a.A[(int64_t)(m0 + m) * a.sm + (int64_t)k * a.sk + (int64_t)to * s.T + t0 + tt];
+        As[tt * G::PAD + m] = w;
       }
-      for (int i = tid; i < kT + kTK - 1; i += 256) {
-        int src = l0 - t0 - (kTK - 1) + i;
-        Hs[i] = (src >= 0 && src < s.Lin) ? Hrow[src] : 0.f;
+      for (int idx = tid; idx < G::XT * (WIN - 1); idx += 256) {
+        const int line = idx / (WIN - 1), i = idx - line * (WIN - 1);
+        const int o = lg * G::XT + line;
+        const int o1 = o / O2, o2 = o - o1 * O2;
+        float x = 0.f;
+        if (o < OUT) {
+          if (FWD) {
+            const int j1 = o1 - t1, j2 = o2 - t2, src = l0 - t0 - (kTK - 1) + i;      // window index of (lj, tt): lj - tt + kTK - 1
+            if (j1 >= 0 && j1 < J1 && j2 >= 0 && j2 < J2 && src >= 0 && src < s.Lin)
+              x = a.X[((((int64_t)b * a.K + k) * J1 + j1) * J2 + j2) * s.Lin + src];
+          } else {
+            const int src = l0 + t0 + i;                                              // window index of (jj, tt): jj + tt
+            if (src < s.L) x = a.X[((((int64_t)b * a.K + k) * s.X1 + (o1 + t1)) * s.X2 + (o2 + t2)) * s.L + src];
+          }
+        }
+        Xs[line * WIN + i] = x;
       }
       __syncthreads();
-      // window index for (lj, tt) is lj - tt + kTK-1
+      const float* xs = Xs + xl * WIN + 4 * lt;
+      const int tmax = min(kTK, s.T - t0);
       float h[4];
-      h[1] = Hs[4 * tx + kTK];
-      h[2] = Hs[4 * tx + kTK + 1];
-      h[3] = Hs[4 * tx + kTK + 2];
+      if (FWD) {
+        h[0] = xs[kTK]; h[1] = xs[kTK + 1]; h[2] = xs[kTK + 2];
+#pragma unroll 8
+        for (int tt = 0; tt < tmax; ++tt) {
+          h[3] = h[2]; h[2] = h[1]; h[1] = h[0];
+          h[0] = xs[kTK - 1 - tt];
+          const float4 av4 = *reinterpret_cast<const float4*>(&As[tt * G::PAD + 4 * ty]);
+          const float av[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
-      for (int tt = 0; tt < kTK; ++tt) {
-        if (tt > 0) { h[3] = h[2]; h[2] = h[1]; h[1] = h[0]; }
-        h[0] = Hs[4 * tx - tt + kTK - 1];
-        float4 a = *reinterpret_cast<const float4*>(&Ws[tt * kLd + 4 * ty]);
-        float av[4] = {a.x, a.y, a.z, a.w};
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], h[j], acc[i][j]);
+        }
+      } else {
+        h[1] = xs[0]; h[2] = xs[1]; h[3] = xs[2];
+#pragma unroll 8
+        for (int tt = 0; tt < tmax; ++tt) {
+          h[0] = h[1]; h[1] = h[2]; h[2] = h[3];
+          h[3] = xs[3 + tt];
+          const float4 av4 = *reinterpret_cast<const float4*>(&As[tt * G::PAD + 4 * ty]);
+          const float av[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], h[j], acc[i][j]);
-      }
-    }
-  }
-
-  const float bm2 = beta - 2.0f, bm1 = beta - 1.0f;
-  float local = 0.f;
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int c = c0 + 4 * ty + i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int l = l0 + 4 * tx + j;
-      if (c < s.C && l < s.L) {
-        int64_t off = ((((int64_t)b * s.C + c) * s.X1 + x1) * s.X2 + x2) * s.L + l;
-        float v = V[off];
-        if (LOSS) {
-          local += loss_term_d<MODE>(v, acc[i][j], beta);
-        } else {
-          float pn, pp;
-          phi_d<MODE>(v, acc[i][j], bm2, bm1, pn, pp);
-          Pn[off] = pn;
-          if (MODE != kKL) Pp[off] = pp;
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], h[j], acc[i][j]);
         }
       }
     }
   }
-  if (LOSS) {
-    double tot = block_sum_d((double)local, red);
-    if (tid == 0)
-      block_partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+
+  const int o = lg * G::XT + xl;
+  if (FWD) {
+    const float bm2 = a.beta - 2.0f, bm1 = a.beta - 1.0f;
+    float local = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = m0 + 4 * ty + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = l0 + 4 * lt + j;
+        if (c < s.C && l < s.L && o < OUT) {
+          const int64_t off = (((int64_t)b * s.C + c) * OUT + o) * s.L + l;
+          const float v = a.V[off];
+          if (LOSS) {
+            local += loss_term_d<MODE>(v, acc[i][j], a.beta);
+          } else {
+            float pn, pp;
+            phi_d<MODE>(v, acc[i][j], bm2, bm1, pn, pp);
+            a.Pn[off] = pn;
+            if (MODE != kKL) a.Pp[off] = pp;
+          }
+        }
+      }
+    }
+    if (LOSS) {
+      const double tot = block_sum_d((double)local, red);
+      if (tid == 0)
+        a.block_partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+    }
+  } else {
+    const int64_t HI = s.h_inner();
+    float* out = a.out + (int64_t)split * s.B * s.R * HI;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = m0 + 4 * ty + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = l0 + 4 * lt + j;
+        if (r < s.R && jj < s.Lin && o < OUT) out[((int64_t)b * s.R + r) * HI + (int64_t)o * s.Lin + jj] = acc[i][j];
+      }
+    }
   }
 }
 
-// grid (ceil(T/64) * R * T1 * T2, ceil(C/64)); thread (ty,tx): c = 4ty.., t = 4tx..
+// ---- wgrad: out[split][c, r, (t1, t2), t] = sum over this split's lines (b, j1, j2) and l of
+//                                              G[b, c, (j1 + t1, j2 + t2), l] H[b, r, (j1, j2), l - t]
+// A block owns MT channels x NCOL columns.  A column is (outer offset, component, offset t): TP = roundup(T, 4) <= 64 offsets
+// of NR components (their H windows are staged once per line) for each of NO outer offsets (each with its own G tile).
+// grid (t tiles * r groups * outer-offset groups, c tiles, nsplit), 256 threads.
+struct WgradPlan { int mt, tp, nr, no, ntt, nrg, nog; };
+
+template <int MT>
 __global__ void __launch_bounds__(256)
-nmfd_wgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restrict__ H,
-                  float* __restrict__ out) {
-  __shared__ __align__(16) float Gs[kTK * kLd];          // Gs[ll][c]
-  __shared__ float Hs[kT + kTK];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int ntt = (s.T + kT - 1) / kT;
-  const int zo = blockIdx.x / ntt;                        // (r, t1, t2)
+nmfd_wgrad_kernel(NmfdShape s, const float* __restrict__ Gm, const float* __restrict__ H, float* __restrict__ out,
+                  int nsplit, WgradPlan p) {
+  using G = Geo<MT>;
+  __shared__ __align__(16) float Gs[G::NTO * kTK * G::PAD];      // Gs[oo][ll][c]
+  __shared__ float Hs[G::HS];
+  const int tid = threadIdx.x, tx = tid % G::TX, ty = tid / G::TX;
+  const int TP = p.tp, NR = p.nr, NO = p.no;
+  const int WIN = TP + kTK;
+  const int col = 4 * tx;                                 // TP is a multiple of 4: a thread's 4 columns share (oo, rl)
+  const int oo = col / (NR * TP), rl = (col - oo * NR * TP) / TP, tl = col - (oo * NR + rl) * TP;
   const int nouter = s.T1 * s.T2;
-  const int r = zo / nouter, to = zo - r * nouter;
-  const int t1 = to / s.T2, t2 = to - t1 * s.T2;
-  const int t0 = (blockIdx.x - zo * ntt) * kT, c0 = blockIdx.y * kT;
+  int bx = blockIdx.x;
+  const int og = bx % p.nog; bx /= p.nog;
+  const int rg = bx % p.nrg;
+  const int t0 = (bx / p.nrg) * TP;
+  const int c0 = blockIdx.y * MT;
+  const int r = rg * NR + rl, to = og * NO + oo;
+  const bool live = oo < NO && to < nouter && r < s.R;
   const int J1 = s.J1(), J2 = s.J2();
   const int64_t VI = s.v_inner();
   float acc[4][4];
@@ -163,149 +251,106 @@ nmfd_wgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int bo = 0; bo < s.B * J1 * J2; ++bo) {            // every H line (b, j1, j2) meets the G line (b, j1 + t1, j2 + t2)
+  // the lines are split over blockIdx.z: more blocks than the output tiles alone give, and shorter fp32 sums
+  const int nlines = s.B * J1 * J2, lps = (nlines + nsplit - 1) / nsplit;
+  const int line0 = blockIdx.z * lps, line1 = min(nlines, line0 + lps);
+  out += (int64_t)blockIdx.z * s.C * s.R * s.w_inner();
+  for (int bo = line0; bo < line1; ++bo) {                // every H line (b, j1, j2) meets the G lines (b, j1 + t1, j2 + t2)
     const int b = bo / (J1 * J2), jo = bo - b * (J1 * J2);
     const int j1 = jo / J2, j2 = jo - j1 * J2;
-    const float* Hrow = H + ((((int64_t)b * s.R + r) * J1 + j1) * J2 + j2) * s.Lin;
-    const float* Gb = G + (int64_t)b * s.C * VI + ((int64_t)(j1 + t1) * s.X2 + (j2 + t2)) * s.L;
+    const float* Hb = H + ((int64_t)b * s.R * J1 * J2 + jo) * s.Lin;           // + r * J1 * J2 * Lin per component
+    const float* Gb = Gm + (int64_t)b * s.C * VI;
     for (int l0 = 0; l0 < s.L; l0 += kTK) {
       __syncthreads();
-      for (int idx = tid; idx < kT * kTK; idx += 256) {
-        int c = idx / kTK, ll = idx - c * kTK;
+      for (int idx = tid; idx < NO * MT * kTK; idx += 256) {
+        const int q = idx / kTK, ll = idx - q * kTK;
+        const int o2 = q / MT, c = q - o2 * MT;
+        const int tq = og * NO + o2;
         float g = 0.f;
-        if (c0 + c < s.C && l0 + ll < s.L) g = Gb[(int64_t)(c0 + c) * VI + l0 + ll];
-        Gs[ll * kLd + c] = g;
+        if (tq < nouter && c0 + c < s.C && l0 + ll < s.L) {
+          const int t1 = tq / s.T2, t2 = tq - t1 * s.T2;
+          g = Gb[(int64_t)(c0 + c) * VI + ((int64_t)(j1 + t1) * s.X2 + (j2 + t2)) * s.L + l0 + ll];
+        }
+        Gs[(o2 * kTK + ll) * G::PAD + c] = g;
       }
-      for (int i = tid; i < kT + kTK - 1; i += 256) {
-        int src = l0 - t0 - (kT - 1) + i;       // window index for (ll, tj) is ll - tj + 63
-        Hs[i] = (src >= 0 && src < s.Lin) ? Hrow[src] : 0.f;
+      for (int idx = tid; idx < NR * (WIN - 1); idx += 256) {
+        const int rr = idx / (WIN - 1), i = idx - rr * (WIN - 1);
+        const int src = l0 - t0 - (TP - 1) + i;           // window index of (ll, tj): ll - tj + TP - 1
+        float h = 0.f;
+        if (rg * NR + rr < s.R && src >= 0 && src < s.Lin) h = Hb[(int64_t)(rg * NR + rr) * J1 * J2 * s.Lin + src];
+        Hs[rr * WIN + i] = h;
       }
       __syncthreads();
-      float h[4];
-      h[0] = Hs[62 - 4 * tx];
-      h[1] = Hs[61 - 4 * tx];
-      h[2] = Hs[60 - 4 * tx];
+      if (live) {
+        const float* hs = Hs + rl * WIN + (TP - 1 - tl);
+        const float* gs = Gs + oo * kTK * G::PAD + 4 * ty;
+        const int lmax = min(kTK, s.L - l0);
+        float h[4];
+        h[0] = hs[-1]; h[1] = hs[-2]; h[2] = hs[-3];       // tl <= TP - 4: the indices are >= 0
+#pragma unroll 8
+        for (int ll = 0; ll < lmax; ++ll) {
+          h[3] = h[2]; h[2] = h[1]; h[1] = h[0];
+          h[0] = hs[ll];
+          const float4 av4 = *reinterpret_cast<const float4*>(&gs[ll * G::PAD]);
+          const float av[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
-      for (int ll = 0; ll < kTK; ++ll) {
-        h[3] = h[2]; h[2] = h[1]; h[1] = h[0];
-        h[0] = Hs[ll + 63 - 4 * tx];
-        float4 a = *reinterpret_cast<const float4*>(&Gs[ll * kLd + 4 * ty]);
-        float av[4] = {a.x, a.y, a.z, a.w};
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], h[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], h[j], acc[i][j]);
+        }
       }
     }
   }
+  if (!live) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int c = c0 + 4 * ty + i;
+    const int c = c0 + 4 * ty + i;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int t = t0 + 4 * tx + j;
+      const int t = t0 + tl + j;
       if (c < s.C && t < s.T) out[(((int64_t)c * s.R + r) * nouter + to) * s.T + t] = acc[i][j];
     }
   }
 }
 
-// grid (ceil(Lin/JTILE) * J1 * J2, nsplit, B); block = RG x JT threads (RG*JT = 256); thread: r = 4rg.., j = 4jx..
-template <int RG>
-__global__ void __launch_bounds__(256)
-nmfd_dgrad_kernel(NmfdShape s, const float* __restrict__ G, const float* __restrict__ W,
-                  float* __restrict__ out, int nsplit) {
-  constexpr int JT = 256 / RG;
-  constexpr int JTILE = 4 * JT;
-  constexpr int Rp = 4 * RG;
-  __shared__ __align__(16) float Ws[kTK * Rp];           // Ws[tt][r]
-  __shared__ float Gs[JTILE + kTK];
-  const int tid = threadIdx.x;
-  const int rg = tid % RG, jx = tid / RG;
-  const int ntj = (s.Lin + JTILE - 1) / JTILE;
-  const int outer = blockIdx.x / ntj;                    // (j1, j2): outer position of this tile of H
-  const int J2 = s.J2();
-  const int j1 = outer / J2, j2 = outer - j1 * J2;
-  const int j0 = (blockIdx.x - outer * ntj) * JTILE, split = blockIdx.y, b = blockIdx.z;
-  const int cps = (s.C + nsplit - 1) / nsplit;
-  const int cbeg = split * cps, cend = min(s.C, cbeg + cps);
-  const int64_t WI = s.w_inner(), RT = (int64_t)s.R * WI, VI = s.v_inner();
-  const int nouter = s.T1 * s.T2;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+inline int row_tile(int n) { return n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 64; }
+inline int xt_of(int mt) { return (256 / (mt / 4)) / 16; }
 
-  for (int co = cbeg * nouter; co < cend * nouter; ++co) {
-    const int c = co / nouter, to = co - c * nouter;
-    const int t1 = to / s.T2, t2 = to - t1 * s.T2;
-    const float* Grow = G + ((int64_t)b * s.C + c) * VI + ((int64_t)(j1 + t1) * s.X2 + (j2 + t2)) * s.L;
-    const float* Wc = W + (int64_t)c * RT + (int64_t)to * s.T;
-    for (int t0 = 0; t0 < s.T; t0 += kTK) {
-      __syncthreads();
-      for (int idx = tid; idx < kTK * Rp; idx += 256) {
-        int r = idx / kTK, tt = idx - r * kTK;
-        float w = 0.f;
-        if (r < s.R && t0 + tt < s.T) w = Wc[(int64_t)r * WI + t0 + tt];
-        Ws[tt * Rp + r] = w;
-      }
-      for (int i = tid; i < JTILE + kTK - 1; i += 256) {
-        int src = j0 + t0 + i;                  // window index for (jj, tt) is jj + tt
-        Gs[i] = (src < s.L) ? Grow[src] : 0.f;
-      }
-      __syncthreads();
-      float g[4];
-      g[1] = Gs[4 * jx];
-      g[2] = Gs[4 * jx + 1];
-      g[3] = Gs[4 * jx + 2];
-#pragma unroll
-      for (int tt = 0; tt < kTK; ++tt) {
-        g[0] = g[1]; g[1] = g[2]; g[2] = g[3];
-        g[3] = Gs[4 * jx + 3 + tt];
-        float4 a = *reinterpret_cast<const float4*>(&Ws[tt * Rp + 4 * rg]);
-        float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], g[j], acc[i][j]);
-      }
-    }
+inline WgradPlan wgrad_plan(const NmfdShape& s) {
+  WgradPlan p;
+  p.mt = row_tile(s.C);
+  const int ncol = 4 * (256 / (p.mt / 4));
+  const int nto = p.mt <= 16 ? 8 : 1;
+  p.tp = (int)round_up(s.T < 64 ? s.T : 64, 4);
+  p.nr = ncol / p.tp;
+  if (p.nr > s.R) p.nr = s.R;
+  if (p.nr < 1) p.nr = 1;
+  p.no = 1;
+  if (p.nr == s.R) {                                       // every component fits: fill the block with outer offsets
+    p.no = ncol / (p.nr * p.tp);
+    if (p.no > nto) p.no = nto;
+    if (p.no > s.T1 * s.T2) p.no = s.T1 * s.T2;
+    if (p.no < 1) p.no = 1;
   }
-  const int64_t HI = s.h_inner();
-  float* o = out + (int64_t)split * s.B * s.R * HI;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int r = 4 * rg + i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int jj = j0 + 4 * jx + j;
-      if (r < s.R && jj < s.Lin) o[((int64_t)b * s.R + r) * HI + (int64_t)outer * s.Lin + jj] = acc[i][j];
-    }
-  }
+  p.ntt = (int)ceil_div(s.T, p.tp);
+  p.nrg = (int)ceil_div(s.R, p.nr);
+  p.nog = (int)ceil_div(s.T1 * s.T2, p.no);
+  return p;
 }
 
-int dgrad_rg(int R) {
-  int rg = 1;
-  while (4 * rg < R) rg <<= 1;
-  return rg;
+dim3 slide_grid(const NmfdShape& s, bool fwd, int mt, int M, int nsplit) {
+  const int64_t out_lines = fwd ? (int64_t)s.X1 * s.X2 : (int64_t)s.J1() * s.J2();
+  const int64_t lout = fwd ? s.L : s.Lin;
+  return dim3((unsigned)(ceil_div(lout, kLT) * ceil_div(out_lines, xt_of(mt))), (unsigned)(ceil_div(M, mt) * nsplit),
+              (unsigned)s.B);
 }
 
-}  // namespace
-
-int nmfd_max_blocks(const NmfdShape& s) {
-  return (int)(ceil_div(s.L, kT) * s.X1 * s.X2 * ceil_div(s.C, kT) * s.B);
-}
-
-int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const float* H, double beta, float* Pn,
-                   float* Pp, double* loss_blocks, int max_blocks, double* loss_dev, cudaStream_t st) {
-  dim3 grid((unsigned)(ceil_div(s.L, kT) * s.X1 * s.X2), (unsigned)ceil_div(s.C, kT), (unsigned)s.B);
-  const int nblocks = (int)(grid.x * grid.y * grid.z);
-  const bool loss = loss_blocks != nullptr;
-  if (loss && nblocks > max_blocks) { set_error("nmfd loss: partial buffer too small"); return 1; }
-  const int mode = beta_mode(beta);
-#define NMFD_GO(M)                                                                                          \
-  if (loss) nmfd_recon_kernel<M, true><<<grid, 256, 0, st>>>(s, V, W, H, (float)beta, Pn, Pp, loss_blocks); \
-  else nmfd_recon_kernel<M, false><<<grid, 256, 0, st>>>(s, V, W, H, (float)beta, Pn, Pp, loss_blocks);
+template <int MT, bool FWD>
+void launch_slide(const NmfdShape& s, const SlideArgs& a, int mode, bool loss, dim3 grid, cudaStream_t st) {
+  if (!FWD) { nmfd_slide_kernel<MT, false, kKL, false><<<grid, 256, 0, st>>>(s, a); return; }
+#define NMFD_GO(M)                                                              \
+  if (loss) nmfd_slide_kernel<MT, true, M, true><<<grid, 256, 0, st>>>(s, a);   \
+  else nmfd_slide_kernel<MT, true, M, false><<<grid, 256, 0, st>>>(s, a);
   switch (mode) {
     case kKL: NMFD_GO(kKL); break;
     case kEU: NMFD_GO(kEU); break;
@@ -313,22 +358,72 @@ int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const flo
     default: NMFD_GO(kGeneric); break;
   }
 #undef NMFD_GO
+}
+
+template <bool FWD>
+void dispatch_slide(int mt, const NmfdShape& s, const SlideArgs& a, int mode, bool loss, dim3 grid, cudaStream_t st) {
+  switch (mt) {
+    case 4: launch_slide<4, FWD>(s, a, mode, loss, grid, st); break;
+    case 8: launch_slide<8, FWD>(s, a, mode, loss, grid, st); break;
+    case 16: launch_slide<16, FWD>(s, a, mode, loss, grid, st); break;
+    case 32: launch_slide<32, FWD>(s, a, mode, loss, grid, st); break;
+    default: launch_slide<64, FWD>(s, a, mode, loss, grid, st); break;
+  }
+}
+
+}  // namespace
+
+int nmfd_max_blocks(const NmfdShape& s) {
+  const dim3 g = slide_grid(s, true, row_tile(s.C), s.C, 1);
+  return (int)((int64_t)g.x * g.y * g.z);
+}
+
+int nmfd_recon_phi(const NmfdShape& s, const float* V, const float* W, const float* H, double beta, float* Pn,
+                   float* Pp, double* loss_blocks, int max_blocks, double* loss_dev, cudaStream_t st) {
+  const int mt = row_tile(s.C);
+  const dim3 grid = slide_grid(s, true, mt, s.C, 1);
+  const int nblocks = (int)((int64_t)grid.x * grid.y * grid.z);
+  const bool loss = loss_blocks != nullptr;
+  if (loss && nblocks > max_blocks) { set_error("nmfd loss: partial buffer too small"); return 1; }
+  SlideArgs a{};
+  a.A = W; a.X = H; a.M = s.C; a.K = s.R; a.sm = (int64_t)s.R * s.w_inner(); a.sk = s.w_inner(); a.nsplit = 1;
+  a.V = V; a.beta = (float)beta; a.Pn = Pn; a.Pp = Pp; a.block_partials = loss_blocks; a.out = nullptr;
+  dispatch_slide<true>(mt, s, a, beta_mode(beta), loss, grid, st);
   NMF_LAUNCH_CHECK();
   if (loss) return sum_partials(loss_blocks, nblocks, loss_dev, st);
   return 0;
 }
 
-int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, cudaStream_t st) {
-  dim3 grid((unsigned)(ceil_div(s.T, kT) * s.R * s.T1 * s.T2), (unsigned)ceil_div(s.C, kT), 1);
-  nmfd_wgrad_kernel<<<grid, 256, 0, st>>>(s, G, H, out);
+int nmfd_wgrad_nsplit(const NmfdShape& s) {
+  const WgradPlan p = wgrad_plan(s);
+  const int64_t tiles = (int64_t)p.ntt * p.nrg * p.nog * ceil_div(s.C, p.mt);
+  int64_t ns = ceil_div(148 * 4, tiles);
+  const int64_t nlines = (int64_t)s.B * s.J1() * s.J2();
+  if (ns > nlines) ns = nlines;
+  if (ns > 64) ns = 64;
+  if (ns < 1) ns = 1;
+  return (int)ns;
+}
+
+int nmfd_wgrad(const NmfdShape& s, const float* G, const float* H, float* out, int nsplit, cudaStream_t st) {
+  const WgradPlan p = wgrad_plan(s);
+  const int ncol = 4 * (256 / (p.mt / 4));
+  if (p.nr * (p.tp + kTK) > (ncol / 4) * (4 + kTK)) { set_error("nmfd_wgrad: internal tile plan exceeds shared memory"); return 1; }
+  dim3 grid((unsigned)((int64_t)p.ntt * p.nrg * p.nog), (unsigned)ceil_div(s.C, p.mt), (unsigned)nsplit);
+  switch (p.mt) {
+    case 4: nmfd_wgrad_kernel<4><<<grid, 256, 0, st>>>(s, G, H, out, nsplit, p); break;
+    case 8: nmfd_wgrad_kernel<8><<<grid, 256, 0, st>>>(s, G, H, out, nsplit, p); break;
+    case 16: nmfd_wgrad_kernel<16><<<grid, 256, 0, st>>>(s, G, H, out, nsplit, p); break;
+    case 32: nmfd_wgrad_kernel<32><<<grid, 256, 0, st>>>(s, G, H, out, nsplit, p); break;
+    default: nmfd_wgrad_kernel<64><<<grid, 256, 0, st>>>(s, G, H, out, nsplit, p); break;
+  }
   NMF_LAUNCH_CHECK();
   return 0;
 }
 
 int nmfd_dgrad_nsplit(const NmfdShape& s) {
-  const int rg = dgrad_rg(s.R);
-  const int jtile = 4 * (256 / rg);
-  int64_t tiles = ceil_div(s.Lin, jtile) * s.J1() * s.J2() * s.B;
+  const dim3 g = slide_grid(s, false, row_tile(s.R), s.R, 1);
+  const int64_t tiles = (int64_t)g.x * g.y * g.z;
   int64_t ns = ceil_div(148 * 4, tiles);
   if (ns > s.C) ns = s.C;
   if (ns > 64) ns = 64;
@@ -338,18 +433,12 @@ int nmfd_dgrad_nsplit(const NmfdShape& s) {
 
 int nmfd_dgrad(const NmfdShape& s, const float* G, const float* W, float* out, int nsplit, cudaStream_t st) {
   if (s.R > 256) { set_error("nmfd_dgrad: rank must be <= 256"); return 1; }
-  const int rg = dgrad_rg(s.R);
-  const int jtile = 4 * (256 / rg);
-  dim3 grid((unsigned)(ceil_div(s.Lin, jtile) * s.J1() * s.J2()), (unsigned)nsplit, (unsigned)s.B);
-  switch (rg) {
-    case 1: nmfd_dgrad_kernel<1><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    case 2: nmfd_dgrad_kernel<2><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    case 4: nmfd_dgrad_kernel<4><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    case 8: nmfd_dgrad_kernel<8><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    case 16: nmfd_dgrad_kernel<16><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    case 32: nmfd_dgrad_kernel<32><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-    default: nmfd_dgrad_kernel<64><<<grid, 256, 0, st>>>(s, G, W, out, nsplit); break;
-  }
+  const int mt = row_tile(s.R);
+  const dim3 grid = slide_grid(s, false, mt, s.R, nsplit);
+  SlideArgs a{};
+  a.A = W; a.X = G; a.M = s.R; a.K = s.C; a.sm = s.w_inner(); a.sk = (int64_t)s.R * s.w_inner(); a.nsplit = nsplit;
+  a.out = out;
+  dispatch_slide<false>(mt, s, a, 0, false, grid, st);
   NMF_LAUNCH_CHECK();
   return 0;
 }
