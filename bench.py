@@ -396,7 +396,8 @@ def sharded_check(dev, rank, world, group, precision):
     err = float(e.max())
     return {"ok": bool(identical and err <= 1.0 and n == iters), "w_replicas_identical": bool(identical),
             "max_err_over_tol": err, "tol": "rtol 1e-3, atol 1e-5*max", "case": f"{N}x{C} R={R} KL {iters} it, "
-            f"{world} row shards vs the single-rank fit", "precision": ms.last_fit_precision}
+            f"{world} row shards vs the single-rank fit", "precision": ms.last_fit_precision,
+            "w_update_path": ms.last_w_update_path}
 
 
 def cfg4_shard_rate(dev, rank, world, group, precision, iters=40):
@@ -617,7 +618,10 @@ def main():
             "metric": "MU iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "step_ms": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"f32": "f32", "f16": "f16", "f16_split": "f16"}.get(precision, precision),
-            "data": "synthetic", "config": workload_config(a.config, beta, world, a.iters, precision),
+            "data": "synthetic", "config": dict(workload_config(a.config, beta, world, a.iters, precision),
+                                                **({"w_update": "fused P2P sum + ratio stage over NVLink peer memory"
+                                                    if getattr(model, "last_w_update_path", None) == "peer" else
+                                                    "NCCL all-reduce between contraction and ratio stage"} if world > 1 else {})),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "gpu_reference": gpu_ref,
         }

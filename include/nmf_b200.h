@@ -125,6 +125,23 @@ int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int 
 int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced,
                         double beta, double gamma, double l1_reg, double l2_reg, void* stream);
 
+/* Row-sharded W update over PEER MEMORY (ranks of one NVLink domain, one process per GPU, 2..8 ranks) -- the fused form of
+ * w_partial -> all-reduce -> w_apply above, without a collective library call on the data path:
+ *   local contraction -> a pack kernel that pushes this rank's partial [C*R | R] into its slot of EVERY rank's exchange block
+ *   (posted NVLink writes) and publishes its iteration counter -> ONE ratio-stage kernel per rank that waits for all counters,
+ *   sums the slots of its own block in rank order (the replicas of W stay bit-identical) and applies nmf.py:78-92.
+ * Setup (once per context, collective): peer_alloc returns this rank's 64-byte CUDA IPC handle; exchange the handles (any
+ * transport; the Python host side uses torch.distributed); peer_connect takes all `world` handles in rank order.  Then every
+ * rank calls update_w_peer for every W update.  peer_supported: 1 if this context / beta can use it (tensor-core path,
+ * rank % 4 == 0, beta != 2).  A rank that never arrives makes the kernel give up after ~2 s; nmfb200_ctx_check_health reports it. */
+int nmfb200_nmf_peer_supported(const nmfb200_ctx* ctx, double beta);
+int nmfb200_nmf_peer_alloc(nmfb200_ctx* ctx, void* ipc_handle_out /* 64 bytes */);
+int nmfb200_nmf_peer_connect(nmfb200_ctx* ctx, int world, int rank, const void* ipc_handles /* world x 64 bytes */);
+int nmfb200_nmf_peer_world(const nmfb200_ctx* ctx);          /* connected ranks, 0 if none */
+int nmfb200_nmf_peer_release(nmfb200_ctx* ctx);
+int nmfb200_nmf_update_w_peer(nmfb200_ctx* ctx, float* W, const float* H,
+                              double beta, double gamma, double l1_reg, double l2_reg, void* stream);
+
 /* Profiling aid for bench.py's roofline line: launches ONLY the fused contraction kernel of the W update
  * (which = 0) or the H update (which = 1) into the engine's scratch, leaving W and H untouched. */
 int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta,

@@ -140,6 +140,12 @@ int nmfb200_ctx_check_health(nmfb200_ctx* ctx, void* stream) {
   if (!ctx) return fail(NMFB200_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return fail(NMFB200_ERR_CUDA, "cannot select the context's device");
+  if (ctx->tc) {
+    const int pr = tc_peer_check(ctx->tc, (cudaStream_t)stream);
+    if (pr > 0) return fail(NMFB200_ERR_STATE, "a sharded W update gave up waiting for rank " + std::to_string(pr - 1) +
+                                               "'s buffer; results are invalid");
+    if (pr < 0) return fail(NMFB200_ERR_CUDA, "stream synchronize failed");
+  }
   return nmfb200_check_health(stream);
 }
 
@@ -400,6 +406,46 @@ int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int 
                          out + RR, st);
   }
   return reduce_chunks(ctx->den, nch, RR, rows, (int)ctx->R, ctx->R, out + RR, st);
+}
+
+/* ---- row-sharded W update over peer memory (NVLink, one process per GPU) ---------------------- */
+
+int nmfb200_nmf_peer_supported(const nmfb200_ctx* ctx, double beta) {
+  if (!ctx || ctx->kind != 0 || !ctx->tc || ctx->tc_off || !ctx->has_target) return 0;
+  return (tc_supports_beta(ctx->tc, beta) && tc_peer_supported(ctx->tc, beta)) ? 1 : 0;
+}
+
+int nmfb200_nmf_peer_alloc(nmfb200_ctx* ctx, void* ipc_handle_out) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->tc) return fail(NMFB200_ERR_STATE, "the peer-memory W update needs the tensor-core path");
+  if (!ipc_handle_out) return fail(NMFB200_ERR_INVALID, "null pointer");
+  return tc_peer_alloc(ctx->tc, ipc_handle_out);
+}
+
+int nmfb200_nmf_peer_connect(nmfb200_ctx* ctx, int world, int rank, const void* ipc_handles) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->tc) return fail(NMFB200_ERR_STATE, "the peer-memory W update needs the tensor-core path");
+  if (!ipc_handles) return fail(NMFB200_ERR_INVALID, "null pointer");
+  return tc_peer_connect(ctx->tc, world, rank, ipc_handles);
+}
+
+int nmfb200_nmf_peer_world(const nmfb200_ctx* ctx) {
+  return (ctx && ctx->kind == 0 && ctx->tc) ? tc_peer_world(ctx->tc) : 0;
+}
+
+int nmfb200_nmf_peer_release(nmfb200_ctx* ctx) {
+  CTX_GUARD(ctx, 0);
+  if (ctx->tc) tc_peer_release(ctx->tc);
+  return 0;
+}
+
+int nmfb200_nmf_update_w_peer(nmfb200_ctx* ctx, float* W, const float* H, double beta, double gamma, double l1_reg,
+                              double l2_reg, void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
+  if (!nmfb200_nmf_peer_supported(ctx, beta)) return fail(NMFB200_ERR_STATE, "peer-memory W update is not available for this context / beta");
+  return tc_update_w_peer(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, (cudaStream_t)stream);
 }
 
 int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced, double beta, double gamma,

@@ -26,6 +26,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -927,6 +928,8 @@ reduce_vconst_kernel(const double* __restrict__ vpart, int64_t nblk, double* __r
 // grid = ceil(rows / rpb); 256 threads = 4 row groups x 64 rank lanes.  Besides the in-place update it emits
 // what the next kernels need: per-block column sums (-> KL denominator of the other factor) and the max
 // (-> power-of-two scale of the fp16 operand copy).
+constexpr int kMaxPeers = 8;      // ranks of one NVLink domain that may share a W update
+
 struct TcApplyArgs {
   float* param; int64_t rows; int R; int rpb;
   const float* num; int nchunks; int64_t chunk_stride; int Rp;     // partial row pitch = padded rank
@@ -936,6 +939,9 @@ struct TcApplyArgs {
   const float* kappa;        // the kernel accumulated sum (P - kappa) G: add kappa * colsum(G) back
   unsigned int* absmax;      // slot to atomicMax into (pre-zeroed)
   int apply;                 // 0: only emit column sums / max of the current values (dirty-factor resync)
+  // Row-sharded W update over peer memory (NVLink): the numerator is the sum, in rank order, of every rank's packed buffer
+  // [rows x R | R or rows x R], read with P2P loads once every rank has published this iteration's counter in `flags`.
+  const float* peers[kMaxPeers]; int npeers; const unsigned int* flags; unsigned int flag_target; unsigned int* peer_err;
 };
 
 __global__ void __launch_bounds__(256)
@@ -1267,6 +1273,35 @@ __device__ __forceinline__ float4 sum_chunks4(const float* __restrict__ p, int n
                      (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
 }
 
+// the same float4 of every rank's packed buffer (slots of THIS rank's exchange block, written by their owners over NVLink),
+// summed in rank order: identical on every rank.  L2 loads: remote writes land in this GPU's L2, never in an SM's L1.
+__device__ __forceinline__ float4 sum_peers4(const float* const* peers, int npeers, int64_t off) {
+  float4 t[kMaxPeers];
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < npeers) t[p] = __ldcg(reinterpret_cast<const float4*>(peers[p] + off));
+  float4 acc = t[0];
+#pragma unroll
+  for (int p = 1; p < kMaxPeers; ++p)
+    if (p < npeers) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
+  return acc;
+}
+
+// one rank's "buffer published" counters, written by the peers over NVLink; bounded wait (a rank that never arrives must not
+// hang the GPU: the error word is checked by the host's health check)
+__device__ __forceinline__ void wait_peer_flags(const unsigned int* flags, int npeers, unsigned int target, unsigned int* err) {
+  if ((int)threadIdx.x < npeers) {
+    const long long t0 = clock64();
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u + threadIdx.x); break; }
+    }
+  }
+  __syncthreads();
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
@@ -1278,17 +1313,25 @@ tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
   const int64_t row1 = min(a.rows, row0 + a.rpb);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   float mx = 0.f;
+  const bool peer = a.npeers > 0;
+  if (peer) wait_peer_flags(a.flags, a.npeers, a.flag_target, a.peer_err);
+  const int64_t RR = a.rows * a.R;               // peer buffers: [rows x R | colsum R (beta 1) or rows x R]
   if (rl < rows_per_pass) {
     float4 kd = make_float4(1.f, 1.f, 1.f, 1.f);
     float kap = 0.f;
-    if (a.apply && !a.den) { kd = *reinterpret_cast<const float4*>(a.kl_den + 4 * q); kap = *a.kappa; }
+    if (a.apply && !a.den) {
+      kd = peer ? sum_peers4(a.peers, a.npeers, RR + 4 * q) : *reinterpret_cast<const float4*>(a.kl_den + 4 * q);
+      kap = *a.kappa;
+    }
     for (int64_t row = row0 + rl; row < row1; row += rows_per_pass) {
       float4* pp = reinterpret_cast<float4*>(a.param + row * a.R) + q;
       float4 v = *pp;
       if (a.apply) {
-        const float4 num = sum_chunks4(a.num + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride);
-        const float4 dsum = a.den ? sum_chunks4(a.den + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 num = peer ? sum_peers4(a.peers, a.npeers, row * a.R + 4 * q)
+                                : sum_chunks4(a.num + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride);
+        const float4 dsum = !a.den ? make_float4(0.f, 0.f, 0.f, 0.f)
+                            : peer ? sum_peers4(a.peers, a.npeers, RR + row * a.R + 4 * q)
+                                   : sum_chunks4(a.den + row * a.Rp + 4 * q, a.nchunks, a.chunk_stride);
         float vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {num.x, num.y, num.z, num.w}, dd[4] = {kd.x, kd.y, kd.z, kd.w};
         const float ds[4] = {dsum.x, dsum.y, dsum.z, dsum.w};
 #pragma unroll
@@ -1382,6 +1425,57 @@ tc_apply_finish_kernel(TcApplyArgs a, TcFinishArgs f) {
       for (int k = 0; k < 128; ++k) dot += prod[k];
       publish_scales(ae, f.which, f.exps, f.absmax_next, dot, f.vconst, f.kappa, f.center, f.bm1, f.bm2, f.cells);
     }
+  }
+}
+
+struct PeerSignal { unsigned int* ticket; unsigned int* const* peer_flags; int world, rank; unsigned int iter; };
+
+// Peer-memory W update, producer side: this rank's packed partial [rows x R | colsum R (beta 1) or rows x R] is PUSHED into
+// slot `rank` of every rank's exchange block (posted NVLink writes; P2P reads of the same data measured 10x slower), then the
+// block that finishes last publishes this rank's iteration counter into every rank's flag array.
+struct PeerPush { float* dst[kMaxPeers]; };
+
+__global__ void __launch_bounds__(256)
+w_pack_push_kernel(const float* __restrict__ num, const float* __restrict__ den, int nchunks, int64_t chunk_stride,
+                   int64_t rows, int R, int Rp, const float* __restrict__ colsum_h, const float* __restrict__ kappa,
+                   PeerPush out, PeerSignal sig) {
+  const int64_t CR = rows * R, total = den ? 2 * CR : CR + R;
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;      // R % 4 == 0: four elements of one row
+  if (i < total) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < CR || den) {
+      const bool second = i >= CR;
+      const int64_t j = second ? i - CR : i;
+      const int64_t row = j / R;
+      const int r = (int)(j - row * R);
+      const float* src = (second ? den : num) + row * Rp + r;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const float4 t = *reinterpret_cast<const float4*>(src + ch * chunk_stride);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      if (!den) {
+        const float k = *kappa;
+        const float4 c = *reinterpret_cast<const float4*>(colsum_h + r);
+        a.x = fmaf(k, c.x, a.x); a.y = fmaf(k, c.y, a.y); a.z = fmaf(k, c.z, a.z); a.w = fmaf(k, c.w, a.w);
+      }
+    } else {
+      a = *reinterpret_cast<const float4*>(colsum_h + (i - CR));
+    }
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < sig.world) *reinterpret_cast<float4*>(out.dst[p] + i) = a;
+  }
+  __shared__ int last;
+  __threadfence_system();                 // this thread's remote writes are performed before the ticket below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last = atomicAdd(sig.ticket, 1u) == gridDim.x - 1;
+    if (last) *sig.ticket = 0u;
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < sig.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sig.peer_flags[threadIdx.x] + sig.rank), "r"(sig.iter) : "memory");
   }
 }
 
@@ -1516,6 +1610,16 @@ Plan make_plan(int64_t Mr, int64_t Nc, int num_sms, int TN) {
 }  // namespace
 
 struct TcState {
+  // ---- row-sharded W update over peer memory (tc_peer_*): one cudaMalloc block per rank, shared by CUDA IPC:
+  //      [64 counters: flags[p] = last iteration rank p published][parity 0: 8 slots][parity 1: 8 slots]; slot p of every
+  //      block is written by rank p (2 C R floats each)
+  void* peer_block = nullptr;                    // this rank's block
+  void* peer_base[kMaxPeers] = {};               // every rank's block in this process' address space (own: peer_block)
+  unsigned int** peer_flag_tab = nullptr;        // device copy of the flag-array pointers (for the signal kernel)
+  unsigned int* peer_err = nullptr;
+  int peer_world = 0, peer_rank = 0;
+  unsigned int peer_iter = 0;
+  int64_t peer_buf_floats = 0;
   int device = 0, num_sms = 148;
   int64_t N = 0, C = 0, R = 0;
   bool split = true;
@@ -1586,8 +1690,19 @@ static void drop_graphs(TcState* s) {
   s->gwarm = false;
 }
 
+void tc_peer_release(TcState* s) {
+  for (int p = 0; p < s->peer_world; ++p)
+    if (p != s->peer_rank && s->peer_base[p]) cudaIpcCloseMemHandle(s->peer_base[p]);
+  for (auto& b : s->peer_base) b = nullptr;
+  cudaFree(s->peer_block); s->peer_block = nullptr;
+  cudaFree(s->peer_flag_tab); s->peer_flag_tab = nullptr;
+  cudaFree(s->peer_err); s->peer_err = nullptr;
+  s->peer_world = 0; s->peer_iter = 0;
+}
+
 void tc_destroy(TcState* s) {
   if (!s) return;      // the caller (capi.cu: free_ctx) has selected s->device
+  tc_peer_release(s);
   drop_graphs(s);
   if (s->gstream) cudaStreamDestroy(s->gstream);
   if (s->gev_in) cudaEventDestroy(s->gev_in);
@@ -1743,7 +1858,7 @@ namespace {
 // buffer [rows*R num | R colsum or rows*R den] instead of this rank's chunked partials.
 int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan* pl, double beta, double gamma,
                      double l1, double l2, cudaStream_t st, const float* reduced = nullptr,
-                     const float* other = nullptr) {
+                     const float* other = nullptr, bool peer = false) {
   const int64_t rows = which == 0 ? s->C : s->N;
   int rpb = (int)round_up(ceil_div(rows, 1024), 4);
   if (rpb < 64) rpb = 64;
@@ -1763,6 +1878,15 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
   }
   a.gamma = (float)gamma; a.l1 = (float)l1; a.l2 = (float)l2;
   a.cs_part = s->cs_part; a.absmax = slot; a.apply = apply ? 1 : 0; a.kappa = reduced ? s->zero : s->kappa;
+  if (peer) {
+    if (!((s->R & 3) == 0 && s->fused_tail)) { set_error("internal: peer W update needs the fused ratio-stage kernel"); return 1; }
+    // the ranks' slots of THIS rank's block for this iteration's parity (every rank pushed its packed partial into them)
+    for (int p = 0; p < s->peer_world; ++p)
+      a.peers[p] = reinterpret_cast<const float*>(s->peer_block) + 64 +
+                   ((int64_t)(s->peer_iter & 1u) * kMaxPeers + p) * s->peer_buf_floats;
+    a.npeers = s->peer_world; a.flags = reinterpret_cast<const unsigned int*>(s->peer_block);
+    a.flag_target = s->peer_iter; a.peer_err = s->peer_err;
+  }
   if ((s->R & 3) == 0 && !(apply && beta == 2.0 && !reduced) && s->fused_tail) {
     // one cooperative launch: ratio stage, grid barrier, operand copy + scalars
     const int lanes = (int)s->R >> 2, rows_per_pass = 256 / lanes;
@@ -2052,6 +2176,97 @@ int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double g
   int rc = apply_and_finish(s, 0, W, true, nullptr, beta, gamma, l1, l2, st, reduced);
   if (rc == 0) s->dirty_w = false;
   return rc;
+}
+
+// ---- row-sharded W update over peer memory --------------------------------------------------------------------------------
+// contraction -> pack kernel that PUSHES this rank's partial into its slot of every rank's exchange block over NVLink and then
+// publishes the iteration counter -> ONE ratio-stage kernel per rank that waits for all counters, sums the slots of its own
+// block in rank order and applies nmf.py:78-92 (tc_apply_finish_kernel).  No collective library call and no reduced copy in
+// between; slots alternate by iteration parity (a rank can be at most one W update ahead of the slowest: its next push needs
+// every rank's counter of the update in between, which that rank publishes after it has read the previous slots).
+bool tc_peer_supported(const TcState* s, double beta) {
+  return (s->R & 3) == 0 && s->fused_tail && tc_supports_partial(s, beta);
+}
+
+int tc_peer_alloc(TcState* s, void* handle_out) {
+  tc_peer_release(s);
+  s->peer_buf_floats = 2 * s->C * s->R;
+  const size_t bytes = (64 + 2 * (size_t)kMaxPeers * (size_t)s->peer_buf_floats) * sizeof(float);
+  NMF_CUDA_CHECK(cudaMalloc(&s->peer_block, bytes));
+  NMF_CUDA_CHECK(cudaMemset(s->peer_block, 0, bytes));
+  NMF_CUDA_CHECK(cudaMalloc(&s->peer_err, 2 * sizeof(unsigned int)));      // [0] wait-timeout record, [1] pack-kernel ticket
+  NMF_CUDA_CHECK(cudaMemset(s->peer_err, 0, 2 * sizeof(unsigned int)));
+  NMF_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  NMF_CUDA_CHECK(cudaIpcGetMemHandle(&h, s->peer_block));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int tc_peer_connect(TcState* s, int world, int rank, const void* handles) {
+  if (!s->peer_block) { set_error("peer_connect before peer_alloc"); return 3; }
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("peer_connect: 2 to 8 ranks"); return 1; }
+  unsigned int* flag_ptrs[kMaxPeers] = {};
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      s->peer_base[p] = s->peer_block;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(handles) + 64 * p, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        s->peer_world = p;             // release what was opened so far
+        s->peer_rank = rank;
+        tc_peer_release(s);
+        set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        return 2;
+      }
+      s->peer_base[p] = ptr;
+    }
+    flag_ptrs[p] = reinterpret_cast<unsigned int*>(s->peer_base[p]);
+  }
+  s->peer_world = world; s->peer_rank = rank; s->peer_iter = 0;
+  NMF_CUDA_CHECK(cudaMalloc(&s->peer_flag_tab, sizeof(flag_ptrs)));
+  NMF_CUDA_CHECK(cudaMemcpy(s->peer_flag_tab, flag_ptrs, sizeof(flag_ptrs), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int tc_peer_world(const TcState* s) { return s->peer_world; }
+
+int tc_update_w_peer(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,
+                     cudaStream_t st) {
+  if (s->peer_world < 2) { set_error("peer W update: peers are not connected"); return 3; }
+  if (!tc_peer_supported(s, beta)) { set_error("peer W update: unsupported rank / beta"); return 1; }
+  int rc = ensure_synced(s, W, H, beta, st);
+  if (rc) return rc;
+  rc = launch_contract(s, 0, beta, st);
+  if (rc) return rc;
+  ++s->peer_iter;
+  const int64_t slot = 64 + ((int64_t)(s->peer_iter & 1u) * kMaxPeers + s->peer_rank) * s->peer_buf_floats;
+  PeerPush push{};
+  for (int p = 0; p < s->peer_world; ++p) push.dst[p] = reinterpret_cast<float*>(s->peer_base[p]) + slot;
+  const int64_t RR = s->C * s->R;
+  const int64_t total = beta == 1.0 ? RR + s->R : 2 * RR;
+  w_pack_push_kernel<<<(unsigned)ceil_div(total, 1024), 256, 0, st>>>(
+      s->part, beta == 1.0 ? nullptr : s->part2, s->plan_w.nchunks, s->C * s->Rp, s->C, (int)s->R, s->Rp,
+      s->colsum + s->R, s->kappa, push, PeerSignal{s->peer_err + 1, s->peer_flag_tab, s->peer_world, s->peer_rank, s->peer_iter});
+  NMF_LAUNCH_CHECK();
+  const float* mine = reinterpret_cast<const float*>(s->peer_block) + slot;       // layout marker for the ratio stage
+  rc = apply_and_finish(s, 0, W, true, nullptr, beta, gamma, l1, l2, st, mine, nullptr, /*peer=*/true);
+  if (rc == 0) s->dirty_w = false;
+  return rc;
+}
+
+// 0: fine; > 0: 1 + the rank whose counter a ratio-stage kernel gave up waiting for (synchronises the stream)
+int tc_peer_check(TcState* s, cudaStream_t st) {
+  if (!s->peer_err) return 0;
+  unsigned int e = 0;
+  if (cudaMemcpyAsync(&e, s->peer_err, sizeof(e), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  if (e) cudaMemsetAsync(s->peer_err, 0, sizeof(e), st);
+  return (int)e;
 }
 
 // debugging aid: report (and clear) a recorded mbarrier wait abort; synchronises the stream

@@ -33,6 +33,17 @@ int tc_w_partial(TcState* s, const float* W, const float* H, double beta, float*
 int tc_raw_terms(TcState* s, int which, const float* W, const float* H, double beta, float* out, cudaStream_t st);
 int tc_w_apply(TcState* s, float* W, const float* reduced, double beta, double gamma, double l1, double l2,
                cudaStream_t st);
+// row-sharded W update over peer memory (one NVLink domain, 2 to 8 ranks): allocate this rank's exchange block and export its
+// 64-byte CUDA IPC handle; open the other ranks' blocks (`handles`: world x 64 bytes, in rank order); then every rank calls
+// tc_update_w_peer for every W update (collective).  tc_peer_check: > 0 if a kernel gave up waiting for a rank.
+bool tc_peer_supported(const TcState* s, double beta);
+int tc_peer_alloc(TcState* s, void* handle_out);
+int tc_peer_connect(TcState* s, int world, int rank, const void* handles);
+int tc_peer_world(const TcState* s);
+void tc_peer_release(TcState* s);
+int tc_update_w_peer(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,
+                     cudaStream_t st);
+int tc_peer_check(TcState* s, cudaStream_t st);
 int tc_contract_only(TcState* s, const float* W, const float* H, int which, double beta, cudaStream_t st);
 // debugging / health: report (and clear) a recorded mbarrier wait abort; synchronises the stream
 int tc_check_wait_abort(cudaStream_t st);

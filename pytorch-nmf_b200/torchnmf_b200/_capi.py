@@ -42,6 +42,12 @@ SIGNATURES = {
     "nmfb200_nmf_raw_terms": (_int, [_vp, _vp, _vp, _int, _dbl, _vp, _vp]),
     "nmfb200_nmf_w_apply": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmf_contract_only": (_int, [_vp, _vp, _vp, _int, _dbl, _vp]),
+    "nmfb200_nmf_peer_supported": (_int, [_vp, _dbl]),
+    "nmfb200_nmf_peer_alloc": (_int, [_vp, _vp]),
+    "nmfb200_nmf_peer_connect": (_int, [_vp, _int, _int, _vp]),
+    "nmfb200_nmf_peer_world": (_int, [_vp]),
+    "nmfb200_nmf_peer_release": (_int, [_vp]),
+    "nmfb200_nmf_update_w_peer": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmfd_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _i64, _i64, _i64, _int]),
     "nmfb200_nmfnd_create": (_int, [_c.POINTER(_vp), _int, _i64, _i64, _int, _c.POINTER(_i64), _i64, _c.POINTER(_i64), _int]),
     "nmfb200_nmfd_set_target": (_int, [_vp, _vp, _vp]),

@@ -11,6 +11,7 @@ needs from its loop body:
 inserts the one collective per iteration that the row-sharded layout needs.
 """
 import ctypes
+import os
 
 import torch
 
@@ -178,6 +179,29 @@ class CudaNmfEngine(_CudaEngine):
         den = buf[rows * self.R:]
         return num, (den if beta == 1 else den.view(rows, self.R))
 
+    # ---- row-sharded W update over peer memory (include/nmf_b200.h: nmfb200_nmf_peer_*) ----
+    def peer_supported(self, beta):
+        return bool(self._lib.nmfb200_nmf_peer_supported(self._ctx, float(beta)))
+
+    def peer_world(self):
+        return int(self._lib.nmfb200_nmf_peer_world(self._ctx))
+
+    def peer_alloc(self):
+        h = (ctypes.c_ubyte * 64)()
+        _capi.check(self._lib.nmfb200_nmf_peer_alloc(self._ctx, ctypes.cast(h, ctypes.c_void_p)))
+        return bytes(h)
+
+    def peer_connect(self, world, rank, handles):
+        buf = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(handles)
+        return int(self._lib.nmfb200_nmf_peer_connect(self._ctx, int(world), int(rank), ctypes.cast(buf, ctypes.c_void_p)))
+
+    def peer_release(self):
+        self._lib.nmfb200_nmf_peer_release(self._ctx)
+
+    def update_w_peer(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_update_w_peer(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                        l2_reg, _stream(self.device)))
+
     def w_apply(self, reduced, beta, gamma, l1_reg, l2_reg):
         _capi.check(self._lib.nmfb200_nmf_w_apply(self._ctx, _ptr(self.W), _ptr(reduced), beta, gamma, l1_reg,
                                                   l2_reg, _stream(self.device)))
@@ -245,6 +269,8 @@ class ShardedEngine:
         self.group = group
         self.kind = local.kind
         self.world = dist.get_world_size(group)
+        self._peer = {}                      # beta -> does the W update run over peer memory
+        self.w_update_path = "nccl"
 
     @property
     def precision(self):
@@ -272,7 +298,39 @@ class ShardedEngine:
         dev = getattr(self.local, "device", None)
         return dev if dev is not None else torch.device("cpu")
 
+    def _peer_ready(self, beta):
+        """Collective, once per (engine, beta): may the W update run over peer memory?  Every rank must answer the same, so
+        each step is agreed with a MIN all-reduce.  Off with NMFB200_PEER=0, on another backend than NCCL, beyond 8 ranks, or
+        when the CUDA IPC handles cannot be opened (ranks on different nodes): the NCCL all-reduce path is used then."""
+        key = float(beta)
+        if key in self._peer:
+            return self._peer[key]
+        dist, loc = self._dist, self.local
+        ok = (os.environ.get("NMFB200_PEER", "1") != "0" and hasattr(loc, "peer_supported") and 2 <= self.world <= 8
+              and dist.get_backend(self.group) == "nccl" and loc.peer_supported(beta))
+        dev = self._reduce_device()
+        connected = bool(ok) and loc.peer_world() == self.world
+        t = torch.tensor([int(bool(ok)), int(connected)], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        ok, connected = bool(t[0].item()), bool(t[1].item())
+        if ok and not connected:
+            mine = torch.frombuffer(bytearray(loc.peer_alloc()), dtype=torch.uint8).to(dev)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            rc = loc.peer_connect(self.world, dist.get_rank(self.group), allh.cpu().numpy().tobytes())
+            t = torch.tensor([int(rc == 0)], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            ok = bool(t[0].item())
+            if not ok:
+                loc.peer_release()
+        self._peer[key] = ok
+        self.w_update_path = "peer" if ok else "nccl"
+        return ok
+
     def update_w(self, beta, gamma, l1_reg, l2_reg):
+        if self._peer_ready(beta):
+            self.local.update_w_peer(beta, gamma, l1_reg, l2_reg)     # contraction -> publish -> fused P2P sum + ratio stage
+            return
         buf = self.local.w_partial(beta)
         self._dist.all_reduce(buf, op=self._dist.ReduceOp.SUM, group=self.group)
         self.local.w_apply(buf, beta, gamma, l1_reg, l2_reg)

@@ -242,6 +242,7 @@ class BaseComponent(torch.nn.Module):
                 W.data.copy_(Wd)
                 H.data.copy_(Hd)
             self.last_fit_precision = eng.precision_for(beta) if hasattr(eng, "precision_for") else eng.precision
+            self.last_w_update_path = getattr(eng, "w_update_path", None)     # sharded fits: "peer" (NVLink P2P) or "nccl"
         finally:
             eng.close()
         return n_iter + 1                                                                  # nmf.py:409
