@@ -125,6 +125,15 @@ int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int 
 int nmfb200_nmf_w_apply(nmfb200_ctx* ctx, float* W, const float* reduced,
                         double beta, double gamma, double l1_reg, double l2_reg, void* stream);
 
+/* Sparse target for beta 1 and beta 2 (nmf.py:603-638 `_nmf_sp_recon_beta_pos_neg`, :95-119): registers V (N x C) in both
+ * compressed forms -- CSR (crow[N+1], col[nnz], val[nnz]) and CSC = CSR of V^T (ccol[C+1], row[nnz], val_t[nnz]) -- int64
+ * indices, fp32 values, device pointers borrowed until the next set_target*.  v_norm_kl / v_norm_eu: `_get_V_norm` nmf.py:161-170
+ * for beta 1 / 2.  update_w / update_h / iterate / loss then evaluate the update terms at the non-zeros only (one warp per row
+ * or column, fp32) and never form the dense product; any other beta returns NMFB200_ERR_INVALID (densify the target). */
+int nmfb200_nmf_set_target_sparse(nmfb200_ctx* ctx, int64_t nnz, const int64_t* crow, const int64_t* col, const float* val,
+                                  const int64_t* ccol, const int64_t* row, const float* val_t,
+                                  double v_norm_kl, double v_norm_eu, void* stream);
+
 /* Row-sharded W update over PEER MEMORY (ranks of one NVLink domain, one process per GPU, 2..8 ranks) -- the fused form of
  * w_partial -> all-reduce -> w_apply above, without a collective library call on the data path:
  *   local contraction -> a pack kernel that pushes this rank's partial [C*R | R] into its slot of EVERY rank's exchange block

@@ -270,6 +270,32 @@ def next_row_cases():
     print(f"wrote reference_next.npz ({os.path.getsize(os.path.join(GOLD, 'reference_next.npz')) / 1e6:.2f} MB)")
 
 
+def sparse_cases():
+    """Sparse-target NMF through the reference's own sparse path (nmf.py:603-638, :95-119), beta 1 and 2 (the branches that
+    never form the dense product), target as in its tests/test_nmf_sparse.py:17-22 (entries above a threshold kept)."""
+    torch.set_num_threads(1)
+    cases = {}
+    N, C, R = 300, 200, 8
+    torch.manual_seed(0)
+    D = torch.rand(N, C)
+    D = torch.where(D > 0.93, D, torch.zeros(()))
+    D[17] = 0                                   # an empty row and an empty column
+    D[:, 5] = 0
+    torch.manual_seed(1)
+    W0, H0 = torch.randn(C, R).abs(), torch.randn(N, R).abs()
+    Vs = D.to_sparse()
+    for beta in (1, 2):
+        for alpha, l1r in ((0, 0), (0.1, 0.5)):
+            W, H, n_iter, losses = run_reference(ref_nmf.NMF, Vs, W0, H0, beta, float("-inf"), 20, alpha, l1r)
+            cases[f"sparse_b{beta}_a{alpha}_l{l1r}"] = dict(
+                kind="nmf", V=D, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                beta=beta, tol=float("-inf"), max_iter=20, alpha=alpha, l1_ratio=l1r)
+        W, H, n_iter, losses = run_reference(ref_nmf.NMF, Vs, W0, H0, beta, 1e-3, 100, 0, 0)
+        cases[f"sparse_b{beta}_stoprule"] = dict(kind="nmf", V=D, W0=W0, H0=H0, W=W, H=H, n_iter=n_iter, losses=losses,
+                                                 beta=beta, tol=1e-3, max_iter=100, alpha=0, l1_ratio=0)
+    save_cases(cases, "reference_sparse.npz")
+
+
 def nd_cases():
     """NMF2D / NMF3D (nmf.py:782-942): ragged sizes, every beta branch, penalties, a batch of 2 and a frozen factor."""
     torch.set_num_threads(1)
@@ -309,9 +335,13 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--r2", action="store_true", help="only the round-2 fixtures (reference_r2.npz)")
     ap.add_argument("--next-rows", action="store_true", help="only the BetaMu / PLCA fixtures (reference_next.npz)")
+    ap.add_argument("--sparse", action="store_true", help="only the sparse-target fixtures (reference_sparse.npz)")
     ap.add_argument("--nd", action="store_true", help="only the NMF2D / NMF3D fixtures (reference_nd.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.sparse:
+        sparse_cases()
+        sys.exit(0)
     if a.nd:
         nd_cases()
         sys.exit(0)

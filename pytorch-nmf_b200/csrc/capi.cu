@@ -40,6 +40,13 @@ struct nmfb200_ctx {
   double* loss_blocks = nullptr;
   int loss_max_blocks = 0;
   float* mm_scratch = nullptr;    // 2048 + 2
+  // sparse target (beta 1 / 2): borrowed CSR (rows of V) and CSC (= CSR of V^T) forms, V_norm of nmf.py:161-170
+  bool sparse = false;
+  const int64_t *sp_crow = nullptr, *sp_col = nullptr, *sp_ccol = nullptr, *sp_row = nullptr;
+  const float *sp_val = nullptr, *sp_val_t = nullptr;
+  double sp_vnorm_kl = 0.0, sp_vnorm_eu = 0.0;
+  float* sp_gram = nullptr;       // [2][R*R] (W^T W, H^T H) + per-block partials
+  double* sp_loss_part = nullptr;
   // NMFD
   float* Pn = nullptr;
   float* Pp = nullptr;
@@ -99,6 +106,7 @@ void free_ctx(nmfb200_ctx* c) {
   if (c->tcd) tc_nmfd_destroy(c->tcd);
   cudaFree(c->num); cudaFree(c->den); cudaFree(c->colsum); cudaFree(c->cs_scratch);
   cudaFree(c->loss_blocks); cudaFree(c->mm_scratch); cudaFree(c->Pn); cudaFree(c->Pp);
+  cudaFree(c->sp_gram); cudaFree(c->sp_loss_part);
   delete c;
 }
 
@@ -224,7 +232,7 @@ int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* 
   CTX_GUARD(ctx, 0);
   if (!V || ldv < ctx->C) return fail(NMFB200_ERR_INVALID, "bad target pointer / leading dimension");
   cudaStream_t st = (cudaStream_t)stream;
-  ctx->V = V; ctx->ldv = ldv; ctx->has_target = true;
+  ctx->V = V; ctx->ldv = ldv; ctx->has_target = true; ctx->sparse = false;
   int rc = matrix_minmax(V, ctx->N, ctx->C, ldv, ctx->mm_scratch, ctx->mm_scratch + 2048, st);
   if (rc) return rc;
   ctx->tc_off = false;
@@ -260,6 +268,79 @@ int nmfb200_nmf_set_target(nmfb200_ctx* ctx, const float* V, int64_t ldv, void* 
   return 0;
 }
 
+/* ---- sparse targets (beta 1 and 2): nmf.py:603-638 without the dense product ------------------------------ */
+
+int nmfb200_nmf_set_target_sparse(nmfb200_ctx* ctx, int64_t nnz, const int64_t* crow, const int64_t* col, const float* val,
+                                  const int64_t* ccol, const int64_t* row, const float* val_t, double v_norm_kl,
+                                  double v_norm_eu, void* stream) {
+  CTX_GUARD(ctx, 0);
+  (void)stream;
+  if (nnz < 0 || !crow || !ccol || (nnz > 0 && (!col || !val || !row || !val_t)))
+    return fail(NMFB200_ERR_INVALID, "bad compressed sparse target");
+  if (!ctx->sp_gram) {
+    const int64_t R = ctx->R;
+    NMF_CUDA_CHECK(cudaMalloc(&ctx->sp_gram, (size_t)(2 * R * R + sparse_gram_part_floats((int)R)) * sizeof(float)));
+    NMF_CUDA_CHECK(cudaMalloc(&ctx->sp_loss_part, (size_t)sparse_loss_blocks(ctx->N) * sizeof(double)));
+  }
+  ctx->sp_crow = crow; ctx->sp_col = col; ctx->sp_val = val; ctx->sp_ccol = ccol; ctx->sp_row = row; ctx->sp_val_t = val_t;
+  ctx->sp_vnorm_kl = v_norm_kl; ctx->sp_vnorm_eu = v_norm_eu;
+  ctx->sparse = true; ctx->has_target = true; ctx->V = nullptr; ctx->tc_off = true;      // the dense kernels are out of play
+  return 0;
+}
+
+namespace {
+// one factor update on the compressed form whose segments are that factor's rows (which = 0: W over CSC, 1: H over CSR)
+int sparse_update(nmfb200_ctx* ctx, int which, float* F, const float* other, double beta, double gamma, double l1_reg,
+                  double l2_reg, cudaStream_t st) {
+  if (beta != 1.0 && beta != 2.0) return fail(NMFB200_ERR_INVALID, "sparse targets: beta must be 1 or 2 (densify the target for other beta)");
+  const int R = (int)ctx->R;
+  const int64_t rows = which == 0 ? ctx->C : ctx->N, orows = which == 0 ? ctx->N : ctx->C;
+  const int64_t* ptr = which == 0 ? ctx->sp_ccol : ctx->sp_crow;
+  const int64_t* idx = which == 0 ? ctx->sp_row : ctx->sp_col;
+  const float* val = which == 0 ? ctx->sp_val_t : ctx->sp_val;
+  int rc = sparse_numerator(ptr, idx, val, F, other, R, rows, beta, ctx->num, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {
+    kl = ctx->colsum + (1 - which) * R;                        // colsum of the OTHER factor, nmf.py:122-131
+    rc = factor_colsum(other, orows, R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);
+  } else {
+    rc = ensure_den(ctx);
+    if (rc) return rc;
+    float* G = ctx->sp_gram + (1 - which) * R * R;             // Gram matrix of the other factor
+    rc = sparse_gram(other, orows, R, ctx->sp_gram + 2 * R * R, G, st);
+    if (rc) return rc;
+    rc = sparse_rows_times_gram(F, G, rows, R, ctx->den, st);  // nmf.py:609
+  }
+  if (rc) return rc;
+  ApplyArgs a{};
+  a.param = F; a.numel = rows * R; a.R = R; a.inner = 1; a.rowlen = R;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = 1; a.chunk_stride = 0;
+  a.ldp = R; a.kl_den = kl; a.out_scale = nullptr;
+  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
+  return apply_update(a, st);
+}
+
+int sparse_loss_ctx(nmfb200_ctx* ctx, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {
+  if (beta != 1.0 && beta != 2.0) return fail(NMFB200_ERR_INVALID, "sparse targets: beta must be 1 or 2");
+  const int R = (int)ctx->R;
+  const float *pa, *pb;
+  int rc;
+  if (beta == 1.0) {
+    rc = factor_colsum(W, ctx->C, R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, ctx->colsum, st);
+    if (rc == 0) rc = factor_colsum(H, ctx->N, R, 1, ctx->cs_scratch, ctx->cs_scratch_floats, ctx->colsum + R, st);
+    pa = ctx->colsum; pb = ctx->colsum + R;
+  } else {
+    rc = sparse_gram(W, ctx->C, R, ctx->sp_gram + 2 * R * R, ctx->sp_gram, st);
+    if (rc == 0) rc = sparse_gram(H, ctx->N, R, ctx->sp_gram + 2 * R * R, ctx->sp_gram + R * R, st);
+    pa = ctx->sp_gram; pb = ctx->sp_gram + R * R;
+  }
+  if (rc) return rc;
+  return sparse_loss(ctx->sp_crow, ctx->sp_col, ctx->sp_val, H, W, R, ctx->N, beta, pa, pb,
+                     beta == 1.0 ? ctx->sp_vnorm_kl : ctx->sp_vnorm_eu, ctx->sp_loss_part, loss_dev, st);
+}
+}  // namespace
+
 int nmfb200_target_minmax(nmfb200_ctx* ctx, float* vmin, float* vmax, void* stream) {
   if (!ctx) return fail(NMFB200_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
@@ -286,6 +367,7 @@ int nmfb200_nmf_update_w(nmfb200_ctx* ctx, float* W, const float* H, double beta
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->sparse) return sparse_update(ctx, 0, W, H, beta, gamma, l1_reg, l2_reg, st);
   if (use_tc(ctx, beta)) return tc_update_w(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, st);
   int rc = simt_contract_w(ctx, W, H, beta, st);
   if (rc) return rc;
@@ -312,6 +394,7 @@ int nmfb200_nmf_update_h(nmfb200_ctx* ctx, const float* W, float* H, double beta
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->sparse) return sparse_update(ctx, 1, H, W, beta, gamma, l1_reg, l2_reg, st);
   if (use_tc(ctx, beta)) return tc_update_h(ctx->tc, W, H, beta, gamma, l1_reg, l2_reg, st);
   int rc = simt_contract_h(ctx, W, H, beta, st);
   if (rc) return rc;
@@ -353,6 +436,7 @@ int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double be
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H || !loss_dev) return fail(NMFB200_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->sparse) return sparse_loss_ctx(ctx, W, H, beta, loss_dev, st);
   if (use_tc(ctx, beta) && tc_supports_loss(ctx->tc, beta)) return tc_loss(ctx->tc, W, H, beta, loss_dev, st);
   return simt_nmf_loss(ctx->V, ctx->ldv, H, W, ctx->N, ctx->C, (int)ctx->R, beta, ctx->loss_blocks,
                        ctx->loss_max_blocks, loss_dev, st);
@@ -367,6 +451,7 @@ int nmfb200_nmf_w_partial(nmfb200_ctx* ctx, const float* W, const float* H, doub
                           void* stream) {
   CTX_GUARD(ctx, 0);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (ctx->sparse) return fail(NMFB200_ERR_STATE, "not available for a sparse target");
   if (!W || !H || !partial) return fail(NMFB200_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(ctx, beta) && tc_supports_partial(ctx->tc, beta)) return tc_w_partial(ctx->tc, W, H, beta, partial, st);
@@ -390,6 +475,7 @@ int nmfb200_nmf_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int 
                           void* stream) {
   CTX_GUARD(ctx, 0);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (ctx->sparse) return fail(NMFB200_ERR_STATE, "not available for a sparse target");
   if (!W || !H || !out || (which != 0 && which != 1)) return fail(NMFB200_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(ctx, beta) && tc_supports_partial(ctx->tc, beta)) return tc_raw_terms(ctx->tc, which, W, H, beta, out, st);
@@ -470,6 +556,7 @@ int nmfb200_nmf_contract_only(nmfb200_ctx* ctx, const float* W, const float* H, 
                               void* stream) {
   CTX_GUARD(ctx, 0);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (ctx->sparse) return fail(NMFB200_ERR_STATE, "not available for a sparse target");
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(ctx, beta)) return tc_contract_only(ctx->tc, W, H, which, beta, st);

@@ -93,6 +93,18 @@ int matrix_minmax(const float* V, int64_t rows, int64_t cols, int64_t ld, float*
 // *out = sum of n doubles in fixed order (single block)
 int sum_partials(const double* p, int n, double* out, cudaStream_t st);
 
+// sparse_nmf.cu ----------------------------------------------------------------------------
+// Sparse-target NMF for beta 1 and 2 (nmf.py:603-638): update terms at the non-zeros of V only, one warp per compressed segment.
+int sparse_numerator(const int64_t* ptr, const int64_t* idx, const float* val, const float* Fself, const float* Fother,
+                     int R, int64_t nseg, double beta, float* out, cudaStream_t st);
+int sparse_gram(const float* F, int64_t rows, int R, float* part, float* out, cudaStream_t st);          // out = F^T F (R x R)
+int64_t sparse_gram_part_floats(int R);
+int sparse_rows_times_gram(const float* F, const float* G, int64_t rows, int R, float* out, cudaStream_t st);
+int sparse_loss(const int64_t* crow, const int64_t* col, const float* val, const float* H, const float* W, int R, int64_t N,
+                double beta, const float* pos_a, const float* pos_b, double v_norm, double* loss_part, double* loss_dev,
+                cudaStream_t st);
+int sparse_loss_blocks(int64_t N);
+
 // nmfd.cu ----------------------------------------------------------------------------------
 // L, T, Lin are the sizes along the LAST (contiguous) axis; NMF2D / NMF3D (nmf.py:782-942) add up to two outer axes of the
 // target (X1, X2), of the kernel (T1, T2) and of H (X - T + 1).  The outer axes are loops around the same sliding GEMMs.

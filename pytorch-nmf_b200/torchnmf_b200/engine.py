@@ -207,6 +207,78 @@ class CudaNmfEngine(_CudaEngine):
                                                   l2_reg, _stream(self.device)))
 
 
+class CudaSparseNmfEngine(_CudaEngine):
+    """NMF on a sparse target, beta 1 or 2 (reference: nmf.py:603-638): V is a coalesced sparse COO tensor (N,C) on the device;
+    its CSR and CSC forms are built here with torch (data-format plumbing) and the update terms are evaluated at the non-zeros
+    only by the library (include/nmf_b200.h: nmfb200_nmf_set_target_sparse)."""
+    kind = "nmf"
+
+    def __init__(self, V, W, H, precision="auto"):
+        super().__init__()
+        self.device = W.device
+        for t, n in ((W, "W"), (H, "H")):
+            _check_f32_cuda(t, n, self.device)
+        assert V.is_sparse and V.is_coalesced() and V.device == W.device
+        N, C = V.shape
+        R = W.shape[1]
+        assert W.shape == (C, R) and H.shape == (N, R)
+        self.W, self.H = W, H
+        vals = V.values().to(torch.float32).contiguous()
+        rows, cols = V.indices()[0].contiguous(), V.indices()[1].contiguous()      # coalesced: sorted by (row, col)
+        nnz = int(vals.numel())
+        self._crow = torch.zeros(N + 1, dtype=torch.int64, device=self.device)
+        self._crow[1:] = torch.cumsum(torch.bincount(rows, minlength=N), 0)
+        order = torch.argsort(cols * N + rows)                                     # the same entries sorted by (col, row)
+        self._ccol = torch.zeros(C + 1, dtype=torch.int64, device=self.device)
+        self._ccol[1:] = torch.cumsum(torch.bincount(cols, minlength=C), 0)
+        self._col, self._val = cols, vals
+        self._row, self._val_t = rows[order].contiguous(), vals[order].contiguous()
+        v64 = vals.double()
+        pos = v64[v64 > 0]
+        self._vnorm_kl = float((pos * pos.log()).sum() - v64.sum())                # nmf.py:166-167 (0 log 0 = 0)
+        self._vnorm_eu = float((v64 * v64).sum() * 0.5)                            # nmf.py:164-165
+        self._vmin = float(vals.min()) if nnz else 0.0
+        self._vmax = float(vals.max()) if nnz else 0.0
+        self._has_zeros = nnz < N * C
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._acquire(("nmf", dev_index, N, C, R, "f32"),
+                      lambda ref: self._lib.nmfb200_nmf_create(ref, dev_index, N, C, R, _capi.PRECISIONS["f32"]))
+        self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.nmfb200_nmf_set_target_sparse(
+            self._ctx, nnz, _ptr(self._crow), _ptr(self._col), _ptr(self._val), _ptr(self._ccol), _ptr(self._row),
+            _ptr(self._val_t), self._vnorm_kl, self._vnorm_eu, _stream(self.device)))
+
+    @property
+    def precision(self):
+        return "f32"
+
+    def precision_for(self, beta):
+        return "f32"
+
+    def minmax(self):
+        return (min(self._vmin, 0.0) if self._has_zeros else self._vmin), self._vmax
+
+    def sync(self):
+        pass
+
+    def update_w(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_update_w(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                   l2_reg, _stream(self.device)))
+
+    def update_h(self, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_update_h(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,
+                                                   l2_reg, _stream(self.device)))
+
+    def iterate(self, n_iter, beta, gamma, l1_reg, l2_reg):
+        _capi.check(self._lib.nmfb200_nmf_iterate(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg, l2_reg,
+                                                  int(n_iter), _stream(self.device)))
+
+    def loss_tensor(self, beta):
+        _capi.check(self._lib.nmfb200_nmf_loss(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
+                                               _stream(self.device)))
+        return self._loss
+
+
 class CudaNmfdEngine(_CudaEngine):
     """NMFD / NMF2D / NMF3D on one GPU: V (B,C,*X), W (C,R,*K), H (B,R,*(X-K+1)) over one to three convolved axes."""
     kind = "nmfd"

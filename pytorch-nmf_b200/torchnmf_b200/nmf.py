@@ -131,6 +131,7 @@ class BaseComponent(torch.nn.Module):
     # can be tested on a GPU-less box.  Deliberately NOT a parameter of `fit`: its signature stays the reference's.
     _engine_factory = None
     _sparse_targets = False       # NMF only (nmf.py:603-638); the convolutive models raise, as in the reference
+    _sparse_kernels = True        # beta 1 / 2 on a sparse target: the library's sparse kernels (False: densify)
 
     @torch.no_grad()
     def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
@@ -154,8 +155,10 @@ class BaseComponent(torch.nn.Module):
             raise NotImplementedError                      # nmf.py:294-295: only NMF derives the sparse update
         if sparse_target:
             # The reference's sparse derivation (nmf.py:95-119, :603-638: SDDMM at the non-zeros) is the same update as the
-            # dense one on V.to_dense() -- its own tests/test_nmf_sparse.py:8-37 asserts exactly that.  There is no SDDMM
-            # kernel here: the target is densified ON THE DEVICE and takes the fused dense path (memory = the dense size).
+            # dense one on V.to_dense() -- its own tests/test_nmf_sparse.py:8-37 asserts exactly that.  beta 1 and 2 run on
+            # the library's sparse kernels (update terms at the non-zeros only, engine.CudaSparseNmfEngine); for any other
+            # beta the reference itself forms WH densely (nmf.py:621-627), and so does this path: the target is densified
+            # ON THE DEVICE and takes the fused dense kernels (memory = the dense size).  `sparse_kernels=False` forces that.
             V = V.coalesce()
             assert torch.all(V.values() >= 0.), "Target should be non-negative."            # nmf.py:329-330
             if beta <= 0:                                                                    # nmf.py:332-336
@@ -174,7 +177,9 @@ class BaseComponent(torch.nn.Module):
             on_gpu = W.device.type == "cuda"
             dev = W.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
             Vd = V.to(dev, non_blocking=True)
-            Vd = (Vd.to_dense() if sparse_target else Vd).to(f32).contiguous()
+            use_sparse_kernels = (sparse_target and beta in (1, 2) and group is None and self._sparse_kernels)
+            if not use_sparse_kernels:
+                Vd = (Vd.to_dense() if sparse_target else Vd).to(f32).contiguous()
             if on_gpu and W.dtype == f32 and H.dtype == f32:
                 Wd, Hd = W.data, H.data                       # updated in place, like param.data in the reference
             else:
@@ -183,7 +188,8 @@ class BaseComponent(torch.nn.Module):
                 Hd = H.data.to(dev, f32, non_blocking=True).contiguous()
             if not Wd.is_contiguous() or not Hd.is_contiguous():
                 raise ValueError("W and H must be contiguous")
-            eng = self._build_engine(Vd, Wd, Hd, precision)
+            eng = (_engine.CudaSparseNmfEngine(Vd.coalesce(), Wd, Hd) if use_sparse_kernels
+                   else self._build_engine(Vd, Wd, Hd, precision))
         else:
             eng = self._engine_factory(V, W.data, H.data)
         if group is not None:

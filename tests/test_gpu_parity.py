@@ -394,3 +394,38 @@ def test_fit_sparse_dense_like_reference(beta, alpha, l1_ratio):
     n2 = sparse.fit(Vs.cuda(), beta, 0, 5, False, alpha, l1_ratio, precision="f32")
     assert n1 == n2
     assert torch.allclose(dense.W, sparse.W) and torch.allclose(dense.H, sparse.H)
+
+
+SP_CASES = load_golden("reference_sparse.npz")
+
+
+@pytest.mark.parametrize("sparse_kernels", [True, False])
+@pytest.mark.parametrize("name", sorted(SP_CASES))
+def test_sparse_target_fit_matches_reference_sparse_golden(name, sparse_kernels):
+    """Fits the reference ran through its sparse path (nmf.py:603-638; 7 % dense, an empty row and column): here on the
+    library's sparse kernels (update terms at the non-zeros only) and on the densified target, same tolerance."""
+    c = SP_CASES[name]
+    m = NMF(W=c["W0"], H=c["H0"]).cuda()
+    m._sparse_kernels = sparse_kernels
+    n_iter = m.fit(c["V"].to_sparse().cuda(), c["beta"], c["tol"], int(c["max_iter"]), False, c["alpha"], c["l1_ratio"],
+                   precision="f32")
+    assert n_iter == c["n_iter"]
+    for got, want, nm in ((m.W.data.cpu(), c["W"], "W"), (m.H.data.cpu(), c["H"], "H")):
+        ok, err = _close(got, want, 2e-4, 1e-6)
+        assert ok, f"{name} {nm}: scaled err {err:.3e}"
+
+
+def test_sparse_kernels_at_scale_match_the_dense_path():
+    """800 x 800 as in the reference's tests/test_nmf_sparse.py:8-37, rank 64 and a rank that is not a multiple of 32."""
+    torch.manual_seed(0)
+    D = torch.rand(800, 800)
+    D = torch.where(D > 0.95, D, torch.zeros(()))
+    for R, beta in ((64, 1), (16, 2), (40, 1)):
+        W0, H0 = torch.rand(800, R) + 0.1, torch.rand(800, R) + 0.1
+        a = NMF(W=W0, H=H0).cuda()
+        a.fit(D.to_sparse().cuda(), beta, 0, 15, False, 0.1, 0.5)
+        b = NMF(W=W0, H=H0).cuda()
+        b.fit(D.cuda(), beta, 0, 15, False, 0.1, 0.5, precision="f32")
+        assert a.last_fit_precision == "f32"
+        assert _close(a.W.data.cpu(), b.W.data.cpu(), 2e-4, 1e-6)[0]
+        assert _close(a.H.data.cpu(), b.H.data.cpu(), 2e-4, 1e-6)[0]

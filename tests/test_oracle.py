@@ -163,3 +163,21 @@ def test_nmfnd_reconstruct_is_the_full_convolution():
     assert torch.allclose(orc.nmfnd_reconstruct(H, W), F.conv2d(H, W.flip((2, 3)), padding=(1, 2)), atol=1e-5)
     H, W = torch.rand(1, 2, 4, 5, 6), torch.rand(3, 2, 2, 2, 3)
     assert torch.allclose(orc.nmfnd_reconstruct(H, W), F.conv3d(H, W.flip((2, 3, 4)), padding=(1, 1, 2)), atol=1e-5)
+
+
+SP_CASES = load_golden("reference_sparse.npz")
+
+
+@pytest.mark.parametrize("name", sorted(SP_CASES))
+def test_oracle_on_the_dense_target_matches_reference_sparse_fit(name):
+    """The reference's sparse path (nmf.py:603-638, :95-119) is the dense update on V.to_dense() (its own
+    tests/test_nmf_sparse.py:8-37): the dense oracle reproduces fits the reference ran on the SPARSE target."""
+    c = SP_CASES[name]
+    torch.set_num_threads(1)
+    W, H, n_iter, losses = orc.fit(c["V"], c["W0"], c["H0"], beta=c["beta"], tol=c["tol"], max_iter=c["max_iter"],
+                                   alpha=c["alpha"], l1_ratio=c["l1_ratio"])
+    assert n_iter == c["n_iter"]
+    assert torch.allclose(W, c["W"], rtol=1e-4, atol=1e-7), (W - c["W"]).abs().max()
+    assert torch.allclose(H, c["H"], rtol=1e-4, atol=1e-7), (H - c["H"]).abs().max()
+    for a, b in zip(losses, c["losses"]):
+        assert math.isclose(a, b, rel_tol=1e-4, abs_tol=1e-5)
