@@ -174,6 +174,17 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H,
                           double beta, double gamma, double l1_reg, double l2_reg, void* stream);
 int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
                       double* loss_dev, void* stream);
+/* The convolutive counterpart of nmfb200_nmf_raw_terms: both backward passes of ONE factor (which = 0: W, 1: H) through
+ * the conv1d / conv2d / conv3d reconstruction (nmf.py:776-779, :862-865, :938-942) from the current W and H, neither
+ * touched.  `out` = raw numerator (the factor's numel), then colsum(other factor) (R, beta == 1) or the raw denominator
+ * (numel).  With W := W * Z this is one EM step's gradients of torchnmf.plca.SIPLCA / SIPLCA2 / SIPLCA3
+ * (plca.py:252-253 with the reconstructions :453-455, :534-537, :621-625), and BetaMu.step for the convolutive modules. */
+int64_t nmfb200_nmfd_raw_terms_numel(const nmfb200_ctx* ctx, int which, double beta);
+int nmfb200_nmfd_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta,
+                           float* out, void* stream);
+/* The caller changed W and / or H in place since the last call (the library keeps fp16 operand copies on the tensor-core
+ * path and refreshes only what it knows changed): refresh both at the next call. */
+int nmfb200_nmfd_sync_factors(nmfb200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -270,6 +270,77 @@ def next_row_cases():
     print(f"wrote reference_next.npz ({os.path.getsize(os.path.join(GOLD, 'reference_next.npz')) / 1e6:.2f} MB)")
 
 
+# PLCA family: the shift-invariant models through the real reference (reference_plca.npz)
+# ---------------------------------------------------------------------------------------------------------
+def plca_cases():
+    import torchnmf.plca as ref_plca
+    torch.set_num_threads(1)
+    flat = {}
+    #      name              class      V shape              R   kernel      iters  ctor kw                    fit kw
+    cases = {
+        "siplca_small":    ("SIPLCA",  (2, 21, 61),          5, (6,),       30, {}, {}),
+        "siplca_prior":    ("SIPLCA",  (2, 21, 61),          5, (6,),       30, {}, dict(W_alpha=1.0005, H_alpha=1.0002, Z_alpha=1.1)),
+        "siplca_sparse":   ("SIPLCA",  (2, 21, 61),          5, (6,),       30, {}, dict(W_alpha=0.9995, H_alpha=0.9995, Z_alpha=0.95)),
+        "siplca_frozenZ":  ("SIPLCA",  (1, 21, 61),          5, (6,),       20, dict(trainable_Z=False), {}),
+        "siplca_frozenW":  ("SIPLCA",  (1, 21, 61),          5, (6,),       20, dict(trainable_W=False), {}),
+        "siplca_onlyH":    ("SIPLCA",  (1, 21, 61),          5, (6,),       20, dict(trainable_W=False, trainable_Z=False), {}),
+        "siplca_stop":     ("SIPLCA",  (1, 21, 61),          5, (6,),       200, {}, dict(tol=1e-2)),
+        "siplca_tc":       ("SIPLCA",  (1, 257, 1024),       16, (32,),     30, {}, {}),
+        "siplca2_small":   ("SIPLCA2", (2, 3, 24, 31),       4, (4, 5),     20, {}, {}),
+        "siplca2_prior":   ("SIPLCA2", (1, 3, 24, 31),       4, (4, 5),     20, {}, dict(W_alpha=1.001, H_alpha=1.0005, Z_alpha=1.05)),
+        "siplca3_small":   ("SIPLCA3", (1, 2, 10, 12, 14),   3, (2, 3, 4),  15, {}, {}),
+    }
+    for name, (cls, vshape, R, K, iters, kw, fitkw) in cases.items():
+        B, C, *X = vshape
+        torch.manual_seed(0)
+        V = torch.rand(*vshape).bfloat16().float() * 3
+        torch.manual_seed(1)
+        W0 = torch.randn(C, R, *K).abs(); H0 = torch.randn(B, R, *(x - k + 1 for x, k in zip(X, K))).abs(); Z0 = torch.rand(R) + 0.1
+        m = getattr(ref_plca, cls)(W=W0, H=H0, Z=Z0, **kw)
+        fitkw = dict(fitkw)
+        tol = fitkw.pop("tol", float("-inf"))
+        n_iter, norm = m.fit(V, tol, iters, False, **fitkw)
+        for k, v in dict(V=V, W0=W0, H0=H0, Z0=Z0, W=m.W.detach().clone(), H=m.H.detach().clone(),
+                         Z=m.Z.detach().clone()).items():
+            flat[f"{name}/{k}"] = v.numpy()
+        flat[f"{name}/n_iter"] = np.array(n_iter); flat[f"{name}/norm"] = np.array(float(norm)); flat[f"{name}/iters"] = np.array(iters)
+        flat[f"{name}/tol"] = np.array(tol, dtype=np.float64)
+        flat[f"{name}/cls"] = np.array(int(cls[-1]) if cls[-1].isdigit() else 1)
+        for k in ("trainable_W", "trainable_H", "trainable_Z"):
+            flat[f"{name}/{k}"] = np.array(int(kw.get(k, True)))
+        for k in ("W_alpha", "H_alpha", "Z_alpha"):
+            flat[f"{name}/{k}"] = np.array(float(fitkw.get(k, 1.0)))
+        print(name, "n_iter", n_iter)
+    # --- BetaMu over the convolutive modules (trainer.py:36-121 with NMFD / NMF2D / NMF3D as the single leaf) ---
+    import torchnmf.trainer as ref_trainer
+    for tag, cls, vshape, R, K in (("nmfd", "NMFD", (2, 21, 61), 5, (6,)), ("nmf2d", "NMF2D", (1, 3, 24, 31), 4, (4, 5)),
+                                   ("nmf3d", "NMF3D", (1, 2, 10, 12, 14), 3, (2, 3, 4))):
+        for beta in (0, 0.5, 1, 2):
+            for reg, (l1, l2, ortho) in (("plain", (0, 0, 0)), ("reg", (0.1, 0.05, 0.2))):
+                if reg == "reg" and beta not in (1, 2):
+                    continue
+                B, C, *X = vshape
+                torch.manual_seed(0)
+                V = torch.rand(*vshape).bfloat16().float() + (2 ** -7 if beta <= 0 else 0.0)
+                torch.manual_seed(1)
+                W0 = torch.randn(C, R, *K).abs(); H0 = torch.randn(B, R, *(x - k + 1 for x, k in zip(X, K))).abs()
+                m = getattr(ref_nmf, cls)(W=W0, H=H0)
+                tr = ref_trainer.BetaMu([m.W, m.H], beta, l1, l2, ortho)
+
+                def closure():
+                    tr.zero_grad()
+                    return V, m()
+                for _ in range(3):
+                    tr.step(closure)
+                name = f"betamu_{tag}_b{beta}_{reg}"
+                for k, v in dict(V=V, W0=W0, H0=H0, W=m.W.detach().clone(), H=m.H.detach().clone(), gH=m.H.grad.clone()).items():
+                    flat[f"{name}/{k}"] = v.numpy()
+                for k, v in dict(beta=beta, l1=l1, l2=l2, ortho=ortho, steps=3, nd=len(K)).items():
+                    flat[f"{name}/{k}"] = np.array(v, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "reference_plca.npz"), **flat)
+    print(f"wrote reference_plca.npz ({os.path.getsize(os.path.join(GOLD, 'reference_plca.npz')) / 1e6:.2f} MB)")
+
+
 def sparse_cases():
     """Sparse-target NMF through the reference's own sparse path (nmf.py:603-638, :95-119), beta 1 and 2 (the branches that
     never form the dense product), target as in its tests/test_nmf_sparse.py:17-22 (entries above a threshold kept)."""
@@ -335,10 +406,14 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--r2", action="store_true", help="only the round-2 fixtures (reference_r2.npz)")
     ap.add_argument("--next-rows", action="store_true", help="only the BetaMu / PLCA fixtures (reference_next.npz)")
+    ap.add_argument("--plca", action="store_true", help="only the SIPLCA / SIPLCA2 / SIPLCA3 fixtures (reference_plca.npz)")
     ap.add_argument("--sparse", action="store_true", help="only the sparse-target fixtures (reference_sparse.npz)")
     ap.add_argument("--nd", action="store_true", help="only the NMF2D / NMF3D fixtures (reference_nd.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.plca:
+        plca_cases()
+        sys.exit(0)
     if a.sparse:
         sparse_cases()
         sys.exit(0)

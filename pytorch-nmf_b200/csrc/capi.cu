@@ -680,47 +680,63 @@ static int nmfd_phi(nmfb200_ctx* c, const float* W, const float* H, double beta,
   return nmfd_recon_phi(c->d, c->V, W, H, beta, c->Pn, c->Pp, nullptr, 0, nullptr, st);
 }
 
+// Both backward passes of one factor (which = 0: W, 1: H) from the current factors, described as the ratio stage's input:
+// split partial numerators (+ denominators for beta != 1), the KL column sums, the centring term of the tensor-core path.
+// Shared by the update (nmf.py:367-391) and by nmfb200_nmfd_raw_terms.  `tc` reports which path produced the terms.
+static int nmfd_terms(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta, ApplyArgs& a, bool* tc,
+                      cudaStream_t st) {
+  const NmfdShape& d = ctx->d;
+  const int64_t inner = which == 0 ? d.w_inner() : d.h_inner();
+  a = ApplyArgs{};
+  a.numel = (int64_t)(which == 0 ? d.C : d.B) * d.R * inner; a.R = d.R; a.inner = inner; a.rowlen = (int64_t)d.R * inner;
+  a.chunk_stride = a.numel; a.ldp = a.rowlen; a.out_scale = nullptr; a.absmax_bits = nullptr;
+  *tc = nmfd_use_tc(ctx, beta);
+  if (*tc) {
+    int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
+    if (rc) return rc;
+    const float* part; int nsplit;
+    rc = which == 0 ? tc_nmfd_wgrad(ctx->tcd, &part, &nsplit, st) : tc_nmfd_dgrad(ctx->tcd, &part, &nsplit, st);
+    if (rc) return rc;
+    a.num = part; a.den = nullptr; a.nchunks = nsplit;
+    const float* cs = tc_nmfd_colsum(ctx->tcd) + (which == 0 ? d.R : 0);       // [colsum_W | colsum_H]
+    a.kl_den = cs; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = cs;
+    return 0;
+  }
+  if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);            // this pass bypasses the tensor-core state
+  int rc = nmfd_phi(ctx, W, H, beta, st);
+  if (rc) return rc;
+  const int nsplit = which == 0 ? ctx->wgrad_nsplit : ctx->dgrad_nsplit;
+  rc = which == 0 ? nmfd_wgrad(d, ctx->Pn, H, ctx->num, nsplit, st) : nmfd_dgrad(d, ctx->Pn, W, ctx->num, nsplit, st);
+  if (rc) return rc;
+  float* kl = nullptr;
+  if (beta == 1.0) {                                     // nmf.py:122-131: column sums of the OTHER factor
+    kl = ctx->colsum + (which == 0 ? d.R : 0);
+    rc = which == 0 ? factor_colsum(H, d.B, d.R, d.h_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st)
+                    : factor_colsum(W, d.C, d.R, d.w_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);
+  } else {
+    rc = which == 0 ? nmfd_wgrad(d, ctx->Pp, H, ctx->den, nsplit, st) : nmfd_dgrad(d, ctx->Pp, W, ctx->den, nsplit, st);
+  }
+  if (rc) return rc;
+  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = nsplit; a.kl_den = kl;
+  return 0;
+}
+
+static int nmfd_update(nmfb200_ctx* ctx, const float* W, const float* H, int which, float* param, double beta, double gamma,
+                       double l1_reg, double l2_reg, cudaStream_t st) {
+  ApplyArgs a; bool tc;
+  int rc = nmfd_terms(ctx, W, H, which, beta, a, &tc, st);
+  if (rc) return rc;
+  a.param = param; a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
+  if (tc) a.absmax_bits = tc_nmfd_begin_update(ctx->tcd, which, st);
+  return apply_update(a, st);
+}
+
 int nmfb200_nmfd_update_w(nmfb200_ctx* ctx, float* W, const float* H, double beta, double gamma, double l1_reg,
                           double l2_reg, void* stream) {
   CTX_GUARD(ctx, 1);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  const NmfdShape& d = ctx->d;
-  if (nmfd_use_tc(ctx, beta)) {
-    int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
-    if (rc) return rc;
-    const float* part; int nsplit;
-    rc = tc_nmfd_wgrad(ctx->tcd, &part, &nsplit, st);
-    if (rc) return rc;
-    ApplyArgs a{};
-    a.param = W; a.numel = (int64_t)d.C * d.R * d.T; a.R = d.R; a.inner = d.T; a.rowlen = (int64_t)d.R * d.T;
-    a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
-    const float* cs = tc_nmfd_colsum(ctx->tcd);
-    a.kl_den = cs + d.R; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = cs + d.R;
-    a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
-    a.absmax_bits = tc_nmfd_begin_update(ctx->tcd, 0, st);
-    return apply_update(a, st);
-  }
-  if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);            // this update bypasses the tensor-core state
-  int rc = nmfd_phi(ctx, W, H, beta, st);
-  if (rc) return rc;
-  rc = nmfd_wgrad(d, ctx->Pn, H, ctx->num, ctx->wgrad_nsplit, st);
-  if (rc) return rc;
-  float* kl = nullptr;
-  if (beta == 1.0) {
-    kl = ctx->colsum + d.R;
-    rc = factor_colsum(H, d.B, d.R, d.h_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);   // nmf.py:122-125
-  } else {
-    rc = nmfd_wgrad(d, ctx->Pp, H, ctx->den, ctx->wgrad_nsplit, st);
-  }
-  if (rc) return rc;
-  ApplyArgs a{};
-  a.param = W; a.numel = (int64_t)d.C * d.R * d.w_inner(); a.R = d.R; a.inner = d.w_inner(); a.rowlen = (int64_t)d.R * d.w_inner();
-  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->wgrad_nsplit; a.chunk_stride = a.numel;
-  a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
-  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
-  return apply_update(a, st);
+  return nmfd_update(ctx, W, H, 0, W, beta, gamma, l1_reg, l2_reg, (cudaStream_t)stream);
 }
 
 int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double beta, double gamma, double l1_reg,
@@ -728,42 +744,36 @@ int nmfb200_nmfd_update_h(nmfb200_ctx* ctx, const float* W, float* H, double bet
   CTX_GUARD(ctx, 1);
   if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
   if (!W || !H) return fail(NMFB200_ERR_INVALID, "null factor pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  const NmfdShape& d = ctx->d;
-  if (nmfd_use_tc(ctx, beta)) {
-    int rc = nmfd_tc_recon(ctx, W, H, false, nullptr, st);
-    if (rc) return rc;
-    const float* part; int nsplit;
-    rc = tc_nmfd_dgrad(ctx->tcd, &part, &nsplit, st);
-    if (rc) return rc;
-    ApplyArgs a{};
-    a.param = H; a.numel = (int64_t)d.B * d.R * d.Lin; a.R = d.R; a.inner = d.Lin; a.rowlen = (int64_t)d.R * d.Lin;
-    a.num = part; a.den = nullptr; a.nchunks = nsplit; a.chunk_stride = a.numel; a.ldp = a.rowlen;
-    const float* cs = tc_nmfd_colsum(ctx->tcd);
-    a.kl_den = cs; a.kappa = tc_nmfd_kappa(ctx->tcd); a.kappa_vec = cs;
-    a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg;
-    a.absmax_bits = tc_nmfd_begin_update(ctx->tcd, 1, st);
-    return apply_update(a, st);
-  }
+  return nmfd_update(ctx, W, H, 1, H, beta, gamma, l1_reg, l2_reg, (cudaStream_t)stream);
+}
+
+int nmfb200_nmfd_sync_factors(nmfb200_ctx* ctx) {
+  CTX_GUARD(ctx, 1);
   if (ctx->tcd) tc_nmfd_mark_dirty(ctx->tcd);
-  int rc = nmfd_phi(ctx, W, H, beta, st);
+  return 0;
+}
+
+int64_t nmfb200_nmfd_raw_terms_numel(const nmfb200_ctx* ctx, int which, double beta) {
+  if (!ctx || ctx->kind != 1 || (which != 0 && which != 1)) return -1;
+  const NmfdShape& d = ctx->d;
+  const int64_t n = (int64_t)(which == 0 ? d.C : d.B) * d.R * (which == 0 ? d.w_inner() : d.h_inner());
+  return beta == 1.0 ? n + d.R : 2 * n;
+}
+
+int nmfb200_nmfd_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int which, double beta, float* out,
+                           void* stream) {
+  CTX_GUARD(ctx, 1);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !out || (which != 0 && which != 1)) return fail(NMFB200_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ApplyArgs a; bool tc;
+  int rc = nmfd_terms(ctx, W, H, which, beta, a, &tc, st);
   if (rc) return rc;
-  rc = nmfd_dgrad(d, ctx->Pn, W, ctx->num, ctx->dgrad_nsplit, st);
+  rc = raw_sum(a, out, a.den ? out + a.numel : nullptr, st);
   if (rc) return rc;
-  float* kl = nullptr;
-  if (beta == 1.0) {
-    kl = ctx->colsum;
-    rc = factor_colsum(W, d.C, d.R, d.w_inner(), ctx->cs_scratch, ctx->cs_scratch_floats, kl, st);     // nmf.py:128-131
-  } else {
-    rc = nmfd_dgrad(d, ctx->Pp, W, ctx->den, ctx->dgrad_nsplit, st);
-  }
-  if (rc) return rc;
-  ApplyArgs a{};
-  a.param = H; a.numel = (int64_t)d.B * d.R * d.h_inner(); a.R = d.R; a.inner = d.h_inner(); a.rowlen = (int64_t)d.R * d.h_inner();
-  a.num = ctx->num; a.den = beta == 1.0 ? nullptr : ctx->den; a.nchunks = ctx->dgrad_nsplit;
-  a.chunk_stride = a.numel; a.ldp = a.rowlen; a.kl_den = kl; a.out_scale = nullptr;
-  a.gamma = (float)gamma; a.l1 = (float)l1_reg; a.l2 = (float)l2_reg; a.absmax_bits = nullptr;
-  return apply_update(a, st);
+  if (beta == 1.0)
+    NMF_CUDA_CHECK(cudaMemcpyAsync(out + a.numel, a.kl_den, (size_t)ctx->d.R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta, double* loss_dev,

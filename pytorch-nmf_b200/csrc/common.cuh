@@ -80,6 +80,8 @@ struct ApplyArgs {
   const float* kappa_vec;     // [R]
 };
 int apply_update(const ApplyArgs& a, cudaStream_t st);
+// num_out[i] (and den_out[i] when a.den) = what the ratio stage would read for element i: summed partials + centring term
+int raw_sum(const ApplyArgs& a, float* num_out, float* den_out, cudaStream_t st);
 // sums[r] = sum over all other dims of x viewed as (outer, R, inner); deterministic two-stage.
 int factor_colsum(const float* x, int64_t outer, int R, int64_t inner, float* scratch, int64_t scratch_floats,
                   float* sums, cudaStream_t st);

@@ -50,6 +50,26 @@ apply_update_kernel(ApplyArgs a) {
   }
 }
 
+// The ratio stage's inputs without the ratio stage: the summed partials (+ the centring term), nothing clamped.
+__global__ void __launch_bounds__(256)
+raw_sum_kernel(ApplyArgs a, float* __restrict__ num_out, float* __restrict__ den_out) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= a.numel) return;
+  const int64_t row = idx / a.rowlen;
+  const int64_t off = row * a.ldp + (idx - row * a.rowlen);
+  const float sc = a.out_scale ? *a.out_scale : 1.0f;
+  float num = 0.f;
+  for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + off];
+  num *= sc;
+  if (a.kappa) num = fmaf(*a.kappa, a.kappa_vec[(int)((idx / a.inner) % a.R)], num);
+  num_out[idx] = num;
+  if (den_out) {
+    float den = 0.f;
+    for (int ch = 0; ch < a.nchunks; ++ch) den += a.den[ch * a.chunk_stride + off];
+    den_out[idx] = den * sc;
+  }
+}
+
 // stage 1 for inner == 1: x is (outer, R) row-major; block b sums a row slab.
 __global__ void __launch_bounds__(256)
 colsum_rows_kernel(const float* __restrict__ x, int64_t outer, int R, int64_t rows_per_block,
@@ -150,6 +170,13 @@ __global__ void minmax_stage2(const float* __restrict__ scratch, int nb, float* 
 int apply_update(const ApplyArgs& a, cudaStream_t st) {
   if (a.numel <= 0) return 0;
   apply_update_kernel<<<(unsigned)ceil_div(a.numel, 256), 256, 0, st>>>(a);
+  NMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int raw_sum(const ApplyArgs& a, float* num_out, float* den_out, cudaStream_t st) {
+  if (a.numel <= 0) return 0;
+  raw_sum_kernel<<<(unsigned)ceil_div(a.numel, 256), 256, 0, st>>>(a, num_out, a.den ? den_out : nullptr);
   NMF_LAUNCH_CHECK();
   return 0;
 }

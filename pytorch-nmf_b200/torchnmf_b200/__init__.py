@@ -4,6 +4,6 @@ __version__ = "0.1.0"
 
 from . import constants, metrics, nmf, plca, trainer  # noqa: F401
 from .nmf import NMF, NMFD, NMF2D, NMF3D, BaseComponent  # noqa: F401
-from .plca import PLCA  # noqa: F401
+from .plca import PLCA, SIPLCA, SIPLCA2, SIPLCA3  # noqa: F401
 from .trainer import BetaMu  # noqa: F401
 from .engine import release_workspaces  # noqa: F401

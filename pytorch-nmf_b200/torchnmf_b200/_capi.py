@@ -55,6 +55,9 @@ SIGNATURES = {
     "nmfb200_nmfd_update_w": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmfd_update_h": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmfd_loss": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
+    "nmfb200_nmfd_raw_terms_numel": (_i64, [_vp, _int, _dbl]),
+    "nmfb200_nmfd_raw_terms": (_int, [_vp, _vp, _vp, _int, _dbl, _vp, _vp]),
+    "nmfb200_nmfd_sync_factors": (_int, [_vp]),
 }
 
 _lib = None

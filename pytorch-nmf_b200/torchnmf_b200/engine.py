@@ -309,7 +309,18 @@ class CudaNmfdEngine(_CudaEngine):
         _capi.check(self._lib.nmfb200_nmfd_set_target(self._ctx, _ptr(V), _stream(self.device)))
 
     def sync(self):
-        pass
+        _capi.check(self._lib.nmfb200_nmfd_sync_factors(self._ctx))
+
+    def raw_terms(self, which, beta):
+        """(numerator, denominator) of the update of W (which=0) or H (which=1) from the CURRENT factors, untouched, in
+        the factor's own shape; the denominator is (R,) for beta == 1 (include/nmf_b200.h: nmfb200_nmfd_raw_terms)."""
+        f = self.W if which == 0 else self.H
+        n = int(self._lib.nmfb200_nmfd_raw_terms_numel(self._ctx, int(which), float(beta)))
+        buf = torch.empty(n, dtype=torch.float32, device=self.device)
+        _capi.check(self._lib.nmfb200_nmfd_raw_terms(self._ctx, _ptr(self.W), _ptr(self.H), int(which), float(beta),
+                                                     _ptr(buf), _stream(self.device)))
+        num, den = buf[:f.numel()].view(f.shape), buf[f.numel():]
+        return num, (den if beta == 1 else den.view(f.shape))
 
     def update_w(self, beta, gamma, l1_reg, l2_reg):
         _capi.check(self._lib.nmfb200_nmfd_update_w(self._ctx, _ptr(self.W), _ptr(self.H), beta, gamma, l1_reg,

@@ -108,7 +108,7 @@ class BaseComponent(torch.nn.Module):
         assert H is not None
         assert W is not None
         out = self.reconstruct(H, W)
-        if own and type(self) is NMF:
+        if own and type(self) in _BETAMU_FUSABLE:
             # the plain reconstruction of this module's own factors: lets trainer.BetaMu recognise a single-leaf graph
             # and take both update terms from the fused kernels instead of two backward passes through `out`
             out._nmf_b200_src = weakref.ref(self)
@@ -370,3 +370,8 @@ class NMF3D(_NMFnD):
     def reconstruct(H, W):
         pad = (W.shape[2] - 1, W.shape[3] - 1, W.shape[4] - 1)
         return F.conv3d(H, W.flip((2, 3, 4)), padding=pad)                                     # nmf.py:938-942
+
+
+# module types whose plain reconstruction trainer.BetaMu may replace by the fused kernels (exact types: a subclass with its
+# own `reconstruct` is a different model)
+_BETAMU_FUSABLE = frozenset({NMF, NMFD, NMF2D, NMF3D})

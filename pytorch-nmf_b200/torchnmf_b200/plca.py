@@ -1,4 +1,4 @@
-"""PLCA with the reference's module surface (torchnmf/plca.py:28-373) and a B200-native `fit`.
+"""PLCA / SIPLCA / SIPLCA2 / SIPLCA3 with the reference's module surface (torchnmf/plca.py:28-625) and a B200-native `fit`.
 
     V (N, C) / sum(V)  ~=  H (N, R) diag(Z (R,)) W (C, R)^T,     W, H column-normalised, Z a distribution.
 
@@ -11,7 +11,9 @@ are two launches of the fused tcgen05 KL contraction (`nmfb200_nmf_raw_terms` wi
 WZH nor P reaches HBM.  dH = dHz * Z and dZ[r] = sum_n H[n, r] dHz[n, r] follow from them; everything after that is the
 reference's sequence of small factor-sized operations (plca.py:256-289).
 
-Only the matrix model `PLCA` is built here; the shift-invariant SIPLCA / SIPLCA2 / SIPLCA3 are out of scope.
+The shift-invariant models (plca.py:376-625) are the same EM step around the convolutive reconstruction
+`sum_{r,t} W[c,r,t] Z[r] H[b,r,x-t]`: the factor pair handed to the library is (W, H Z) as well, and the two gradients are
+the sliding contractions of `nmfb200_nmfd_raw_terms` (wgrad and dgrad of the ratio tile; csrc/nmfd.cu, csrc/tc_nmfd.cu).
 """
 import math
 from collections.abc import Iterable as _Iterable
@@ -24,12 +26,14 @@ from torch.nn import Parameter
 from .constants import eps
 from . import engine as _engine
 
+from torch.nn.modules.utils import _single, _pair, _triple
+
 try:
     from tqdm import tqdm as _tqdm
 except Exception:  # pragma: no cover
     _tqdm = None
 
-__all__ = ["PLCA", "BaseComponent"]
+__all__ = ["PLCA", "SIPLCA", "SIPLCA2", "SIPLCA3", "BaseComponent"]
 
 
 @torch.no_grad()
@@ -140,23 +144,26 @@ class BaseComponent(torch.nn.Module):
         Vfull = Vn * normd
 
         def loss_now():
-            WZH = (Hd * Zd) @ Wd.t()
+            WZH = self.reconstruct(Hd, Wd, Zd)
             d = float(_kl(WZH * normd, Vfull))
             return math.sqrt(2.0 * d) if d >= 0 else float("nan")                           # plca.py:245-246,293-294
 
-        Hz = (Hd * Zd).contiguous()                   # the engine's row factor: H diag(Z)
-        eng = _engine.CudaNmfEngine(Vn, Wd, Hz, precision)
+        def over(z, x):                               # a rank vector against the rank dimension (1) of a factor
+            return z[(slice(None),) + (None,) * (x.dim() - 2)]                               # plca.py:269-270,282-283
+
+        Hz = (Hd * over(Zd, Hd)).contiguous()         # the engine's activation factor: H diag(Z)
+        eng = self._engine(Vn, Wd, Hz, precision)
         try:
             loss_init = previous_loss = loss_now()
             bar = _tqdm(total=max_iter, disable=not verbose) if _tqdm is not None else None
             n_iter = -1
             for n_iter in range(max_iter):
-                torch.mul(Hd, Zd, out=Hz)
+                torch.mul(Hd, over(Zd, Hd), out=Hz)
                 eng.sync()
-                dW, _ = eng.raw_terms(0, 1.0)         # sum_n P (H Z)          = W.grad   (plca.py:252-253)
-                dHz, _ = eng.raw_terms(1, 1.0)        # sum_c P W;  H.grad = dHz * Z,  Z.grad = sum_n H dHz
-                dH = dHz * Zd
-                dZ = (Hd * dHz).sum(0)
+                dW, _ = eng.raw_terms(0, 1.0)         # P contracted with H Z  = W.grad   (plca.py:252-253)
+                dHz, _ = eng.raw_terms(1, 1.0)        # P contracted with W;  H.grad = dHz * Z,  Z.grad = sum H dHz
+                dH = dHz * over(Zd, Hd)
+                dZ = get_norm(Hd * dHz).reshape(-1)
                 Z_prior = None
                 if Z.requires_grad:                                                          # plca.py:256-262
                     Zd.mul_(dZ.clamp_min(0))
@@ -171,7 +178,7 @@ class BaseComponent(torch.nn.Module):
                         W_div = get_norm(Wd)
                         Z_prior = W_div.squeeze()
                     else:
-                        W_div = Z_prior
+                        W_div = over(Z_prior, Wd)
                     Wd.div_(W_div)
                     if not _is_one(W_alpha):
                         Wd.add_(_as(W_alpha, Wd) - 1)
@@ -179,7 +186,7 @@ class BaseComponent(torch.nn.Module):
                         Wd.div_(get_norm(Wd))
                 if H.requires_grad:                                                          # plca.py:277-288
                     Hd.mul_(dH.clamp_min(0))
-                    H_div = get_norm(Hd) if Z_prior is None else Z_prior
+                    H_div = get_norm(Hd) if Z_prior is None else over(Z_prior, Hd)
                     Hd.div_(H_div)
                     if not _is_one(H_alpha):
                         Hd.add_(_as(H_alpha, Hd) - 1)
@@ -202,6 +209,11 @@ class BaseComponent(torch.nn.Module):
         if stage:
             W.data.copy_(Wd); H.data.copy_(Hd); Z.data.copy_(Zd)
         return n_iter, norm                                                                  # plca.py:304
+
+
+    @staticmethod
+    def _engine(Vn, W, Hz, precision):
+        raise NotImplementedError
 
 
 def _is_one(a):
@@ -227,3 +239,78 @@ class PLCA(BaseComponent):
     @staticmethod
     def reconstruct(H, W, Z):
         return H @ (W * Z).t()                       # plca.py:371-373
+
+    @staticmethod
+    def _engine(Vn, W, Hz, precision):
+        return _engine.CudaNmfEngine(Vn, W, Hz, precision)
+
+
+class _ShiftInvariant(BaseComponent):
+    """The shift-invariant models: V (B, C, *X), W (C, R, *K), H (B, R, *(X - K + 1)), Z (R,)."""
+
+    @staticmethod
+    def _engine(Vn, W, Hz, precision):
+        return _engine.CudaNmfdEngine(Vn, W, Hz, precision)
+
+
+def _flip_conv(conv, H, W, Z):
+    # plca.py:453-455, :534-537, :621-625: full-padding convolution with the flipped kernel, the prior on the rank axis
+    nd = W.dim() - 2
+    kernel = W.flip(tuple(range(2, 2 + nd))) * Z.view(-1, *([1] * nd))
+    return conv(H, kernel, padding=tuple(k - 1 for k in W.shape[2:]))
+
+
+class SIPLCA(_ShiftInvariant):
+    """Shift-invariant PLCA along one axis (reference: plca.py:376-455).
+    V (B, C, L), W (C, R, T), H (B, R, L - T + 1), Z (R,):  P(b, c, l) ~= sum_z sum_t P(c, t | z) P(z) P(b, l - t | z)."""
+
+    def __init__(self, Vshape=None, rank=None, T=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            T, = _single(T)
+            batch, K, M = Vshape
+            rank = rank if rank else K
+            kwargs["W"] = (K, rank, T)
+            kwargs["H"] = (batch, rank, M - T + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W, Z):
+        return _flip_conv(F.conv1d, H, W, Z)
+
+
+class SIPLCA2(_ShiftInvariant):
+    """Shift-invariant PLCA along two axes (reference: plca.py:458-537).
+    V (B, C, L, M), W (C, R, k0, k1), H (B, R, L - k0 + 1, M - k1 + 1), Z (R,)."""
+
+    def __init__(self, Vshape=None, rank=None, kernel_size=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            kernel_size = _pair(kernel_size)
+            k0, k1 = kernel_size
+            batch, channel, K, M = Vshape
+            rank = rank if rank else K
+            kwargs["W"] = (channel, rank) + kernel_size
+            kwargs["H"] = (batch, rank, K - k0 + 1, M - k1 + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W, Z):
+        return _flip_conv(F.conv2d, H, W, Z)
+
+
+class SIPLCA3(_ShiftInvariant):
+    """Shift-invariant PLCA along three axes (reference: plca.py:540-625).
+    V (B, C, L, M, O), W (C, R, k0, k1, k2), H (B, R, L - k0 + 1, M - k1 + 1, O - k2 + 1), Z (R,)."""
+
+    def __init__(self, Vshape=None, rank=None, kernel_size=1, **kwargs):
+        if isinstance(Vshape, _Iterable):
+            kernel_size = _triple(kernel_size)
+            k0, k1, k2 = kernel_size
+            batch, channel, N, K, M = Vshape
+            rank = rank if rank else K
+            kwargs["W"] = (channel, rank) + kernel_size
+            kwargs["H"] = (batch, rank, N - k0 + 1, K - k1 + 1, M - k2 + 1)
+        super().__init__(rank, **kwargs)
+
+    @staticmethod
+    def reconstruct(H, W, Z):
+        return _flip_conv(F.conv3d, H, W, Z)

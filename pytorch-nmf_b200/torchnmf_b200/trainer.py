@@ -14,7 +14,9 @@ Two ways to obtain the two gradient terms `neg = relu(d<WH, V (WH+eps)^(beta-2)>
 * fused (B200): when the prediction is the plain reconstruction of ONE `torchnmf_b200.NMF` module on a CUDA device and `p`
   is that module's W or H, both terms come from ONE launch of the fused tcgen05 contraction
   (`nmfb200_nmf_raw_terms`): neither WH nor the ratio matrices are materialised by the update.  The closure may
-  return the module itself instead of its output (`return V, model`) to skip the forward pass as well.
+  return the module itself instead of its output (`return V, model`) to skip the forward pass as well.  The
+  convolutive modules (`NMFD`, `NMF2D`, `NMF3D`) take the same route through `nmfb200_nmfd_raw_terms` (the sliding
+  contractions of csrc/nmfd.cu / csrc/tc_nmfd.cu instead of two passes through cuDNN's convolution backward).
 """
 import weakref
 
@@ -72,19 +74,24 @@ class _FusedTerms:
         W, H = module.W, module.H
         if W is None or H is None or (p is not W and p is not H):
             return None
-        if not (V.is_cuda and V.dim() == 2 and not V.is_sparse and V.dtype == torch.float32):
+        nd = W.dim() - 2                                  # convolved axes: 0 for NMF, 1..3 for NMFD / NMF2D / NMF3D
+        if not (V.is_cuda and not V.is_sparse and V.dtype == torch.float32 and 0 <= nd <= 3 and V.dim() == W.dim()):
             return None
         if not (W.is_cuda and H.is_cuda and W.dtype == torch.float32 and H.dtype == torch.float32
-                and W.device == V.device and H.device == V.device and W.dim() == 2 and H.dim() == 2
+                and W.device == V.device and H.device == V.device and H.dim() == W.dim()
                 and W.data.is_contiguous() and H.data.is_contiguous()):
             return None
-        if V.shape != (H.shape[0], W.shape[0]) or W.shape[1] > 256:
+        if W.shape[1] != H.shape[1] or W.shape[1] > 256:
+            return None
+        want = (H.shape[0], W.shape[0]) + tuple(j + k - 1 for j, k in zip(H.shape[2:], W.shape[2:]))
+        if tuple(V.shape) != want:
             return None
         Vc = V if V.is_contiguous() else V.contiguous()
         key = (id(module), Vc.data_ptr(), Vc._version, tuple(Vc.shape), W.data_ptr(), H.data_ptr())
         if key != self._key:
             self.close()
-            self._eng = _engine.CudaNmfEngine(Vc, W.data, H.data, "auto")
+            make = _engine.CudaNmfEngine if nd == 0 else _engine.CudaNmfdEngine
+            self._eng = make(Vc, W.data, H.data, "auto")
             self._key = key
             self._keep = Vc            # the engine borrows the target's storage
         else:
@@ -92,7 +99,7 @@ class _FusedTerms:
         which = 0 if p is W else 1
         num, den = self._eng.raw_terms(which, beta)
         if beta == 1:                  # trainer.py:83-84: backward of ones = column sums of the other factor
-            den = den.expand_as(num)
+            den = den.view(1, -1, *([1] * nd)).expand_as(num) if nd else den.expand_as(num)
         return num, den
 
 
