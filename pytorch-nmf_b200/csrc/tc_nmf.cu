@@ -1682,7 +1682,8 @@ struct TcState {
 };
 
 bool tc_shape_supported(int64_t N, int64_t C, int64_t R) {
-  return R >= 1 && R <= 128 && N >= 1 && C >= 1 && N < (1ll << 31) && C < (1ll << 31);
+  // the conversion kernel walks 64-row slabs on gridDim.y (<= 65535): taller targets take the fp32 kernels
+  return R >= 1 && R <= 128 && N >= 1 && C >= 1 && N <= 65535ll * 64 && C < (1ll << 31);
 }
 
 static void drop_graphs(TcState* s) {

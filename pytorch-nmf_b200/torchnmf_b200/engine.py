@@ -36,9 +36,35 @@ def _check_f32_cuda(t, name, device):
 
 
 # Engine workspaces (the fp16 operand copies of V are the size of V) are kept across fit() calls of the same
-# shape instead of being cudaMalloc'ed / cudaFree'd every time.  release_workspaces() drops them.
+# shape instead of being cudaMalloc'ed / cudaFree'd every time.  The memory is cudaMalloc'ed by the library, i.e. invisible
+# to torch's caching allocator, so the cache is bounded by BYTES (estimated from the shapes): at most
+# NMFB200_WORKSPACE_CACHE_MB (default 8192; 0 disables caching) are held between fits, in at most _MAX_WORKSPACES
+# contexts.  release_workspaces() drops them all.
 _WORKSPACES = {}
 _MAX_WORKSPACES = 2
+_CACHE_BYTES = int(float(os.environ.get("NMFB200_WORKSPACE_CACHE_MB", "8192")) * (1 << 20))
+
+
+def _workspace_bytes(key):
+    """Upper estimate of the device memory a cached context of this key holds."""
+    if key[0] == "nmf":                   # ("nmf", device, N, C, R, precision): V16 + Vt16 + split partials + fp32 scratch
+        _, _, N, C, R = key[:5]
+        return 4 * N * C + 64 * (N + C) * max(R, 64)
+    if key[0] == "nmfd":                  # ("nmfd", device, B, C, X, R, K, precision): ratio tiles + shifted operand copies
+        _, _, B, C, X, R, K = key[:7]
+        nx, nk = 1, 1
+        for x in X:
+            nx *= x
+        for k in K:
+            nk *= k
+        return 12 * B * C * nx + 64 * C * R * nk + 64 * B * R * nx
+    return 0
+
+
+def cached_workspace_bytes():
+    """Estimated device memory currently parked in the workspace cache."""
+    return sum(_workspace_bytes(k) for k in _WORKSPACES)
+
 
 
 def release_workspaces():
@@ -70,8 +96,10 @@ class _CudaEngine:
 
     def close(self):
         if self._ctx:
-            if self._key is not None:
-                while len(_WORKSPACES) >= _MAX_WORKSPACES:
+            mine = _workspace_bytes(self._key) if self._key is not None else 0
+            if self._key is not None and mine <= _CACHE_BYTES:
+                while _WORKSPACES and (len(_WORKSPACES) >= _MAX_WORKSPACES
+                                       or cached_workspace_bytes() + mine > _CACHE_BYTES):
                     old = _WORKSPACES.pop(next(iter(_WORKSPACES)))
                     self._lib.nmfb200_destroy(old)
                 _WORKSPACES[self._key] = self._ctx

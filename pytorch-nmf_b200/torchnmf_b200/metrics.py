@@ -6,7 +6,7 @@ import torch
 
 from .constants import eps
 
-__all__ = ["kl_div", "euclidean", "is_div", "beta_div"]
+__all__ = ["kl_div", "euclidean", "is_div", "beta_div", "sparseness"]
 
 
 def kl_div(input, target):
@@ -42,3 +42,9 @@ def beta_div(input, target, beta=2):
         t = t + eps
     bm = beta - 1
     return (t.pow(beta).sum() + bm * x.pow(beta).sum() - beta * (t @ x.pow(bm))) / (beta * bm)
+
+
+def sparseness(x):
+    """Hoyer's sparseness measure (sqrt(N) - |x|_1 / |x|_2) / (sqrt(N) - 1) of a tensor of any shape (metrics.py:99-115)."""
+    n = x.numel() ** 0.5
+    return (n - x.norm(1) / x.norm(2)) / (n - 1)
