@@ -186,6 +186,18 @@ int nmfb200_nmfd_raw_terms(nmfb200_ctx* ctx, const float* W, const float* H, int
  * path and refreshes only what it knows changed): refresh both at the next call. */
 int nmfb200_nmfd_sync_factors(nmfb200_ctx* ctx);
 
+/* ---- sparseness-constrained NMF (Hoyer 2004) --------------------------------------------- */
+
+/* Replaces torchnmf.nmf._proj_func (nmf.py:21-49) and the Python loops that call it once per component
+ * (sparse_fit nmf.py:462-465, :472-475, :519-522, :565-568; trainer.SparsityProj.step trainer.py:176-181): every slice
+ * x[:, j, :] of the fp32 device tensor x viewed as (outer, D, inner) is replaced IN PLACE by the closest non-negative
+ * vector with L1 norm k1[j] and squared L2 norm k2[j] (k1, k2: D device floats).  The reference's data-dependent loop
+ * (one host synchronisation per round and slice) runs on the device, one block per slice, one launch for all D slices.
+ * zeroed_ws: D * outer * inner bytes of device scratch.  Context-free: runs on CUDA device `device`, the caller's
+ * current device is restored. */
+int nmfb200_hoyer_project(int device, float* x, int64_t outer, int64_t D, int64_t inner, const float* k1, const float* k2,
+                          void* zeroed_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -399,6 +399,89 @@ def nd_cases():
     save_cases(cases, "reference_nd.npz")
 
 
+# Sparseness-constrained path (Hoyer 2004): _proj_func, sparse_fit, SparsityProj through the real reference
+# ---------------------------------------------------------------------------------------------------------
+def hoyer_cases():
+    import torchnmf.trainer as ref_trainer
+    from torchnmf.metrics import beta_div as ref_beta_div
+    torch.set_num_threads(1)
+    flat = {}
+
+    def put(name, tensors, scalars):
+        for k, v in tensors.items():
+            flat[f"{name}/{k}"] = v.detach().numpy().copy()
+        for k, v in scalars.items():
+            flat[f"{name}/{k}"] = np.array(v, dtype=np.float64)
+
+    # --- _proj_func on the slices of a parameter viewed as (outer, D, inner): unit-norm form and the line-search form ---
+    for name, shape, dim, sp in (("proj_cols", (83, 8), 1, 0.5), ("proj_sparse", (257, 6), 1, 0.9),
+                                 ("proj_slabs", (21, 4, 5), 1, 0.6), ("proj_dense", (64, 3), 1, 0.05),
+                                 ("proj_big", (4099, 5), 1, 0.7), ("proj_dim0", (4, 300), 0, 0.8)):
+        torch.manual_seed(3)
+        X = torch.randn(*shape).abs() + 0.01
+        if name == "proj_dim0":
+            X[1] = torch.randn(300)                      # a slice with negative entries (a gradient step can produce them)
+        D = shape[dim]
+        n = X.numel() // D
+        L1 = n ** 0.5 * (1 - sp) + sp
+        norms = ref_nmf._get_norm(X, dim)
+        for form, (k1, k2) in (("unit", ([L1] * D, [1.0] * D)),
+                               ("scaled", ((L1 * norms).tolist(), (norms ** 2).tolist()))):
+            Y = X.clone()
+            for j in range(D):
+                sl = (slice(None),) * dim + (j,)
+                Y[sl] = ref_nmf._proj_func(X[sl].clone(), float(k1[j]), float(k2[j]))
+            put(f"{name}_{form}", dict(X=X, Y=Y, k1=torch.tensor(k1, dtype=torch.float64),
+                                       k2=torch.tensor(k2, dtype=torch.float64)), dict(dim=dim))
+
+    # --- sparse_fit (nmf.py:411-599) ---
+    def run_sfit(name, cls, vshape, wshape, hshape, beta, iters, sW, sH, **kw):
+        V, W0, H0 = make_inputs(vshape, wshape, hshape, floor=2 ** -7 if beta <= 0 else 0.0)
+        m = cls(W=W0, H=H0, **kw)
+        n_iter = m.sparse_fit(V, beta, iters, False, sW, sH)
+        put(name, dict(V=V, W0=W0, H0=H0, W=m.W, H=m.H),
+            dict(beta=beta, iters=iters, n_iter=n_iter, sW=-1 if sW is None else sW, sH=-1 if sH is None else sH,
+                 trainable_W=int(kw.get("trainable_W", True)), trainable_H=int(kw.get("trainable_H", True))))
+
+    N, C, R = 97, 83, 8
+    nmf = ref_nmf.NMF
+    run_sfit("sfit_nmf_sW", nmf, (N, C), (C, R), (N, R), 2, 25, 0.5, None)
+    run_sfit("sfit_nmf_sH", nmf, (N, C), (C, R), (N, R), 2, 25, None, 0.4)
+    run_sfit("sfit_nmf_both", nmf, (N, C), (C, R), (N, R), 2, 25, 0.6, 0.3)
+    run_sfit("sfit_nmf_kl_sW", nmf, (N, C), (C, R), (N, R), 1, 25, 0.3, None)      # (KL with both constraints ends in NaN in the reference)
+    run_sfit("sfit_nmf_b15_both", nmf, (N, C), (C, R), (N, R), 1.5, 20, 0.5, 0.4)
+    run_sfit("sfit_nmf_b05_sH", nmf, (N, C), (C, R), (N, R), 0.5, 20, None, 0.4)
+    run_sfit("sfit_nmf_none", nmf, (N, C), (C, R), (N, R), 1, 20, None, None)
+    run_sfit("sfit_nmf_frozenW", nmf, (N, C), (C, R), (N, R), 2, 20, 0.5, 0.4, trainable_W=False)
+    run_sfit("sfit_nmf_frozenH", nmf, (N, C), (C, R), (N, R), 2, 20, 0.5, 0.4, trainable_H=False)
+    run_sfit("sfit_nmf_mid", nmf, (1024, 512), (512, 32), (1024, 32), 2, 12, 0.5, 0.4)
+    run_sfit("sfit_nmfd_sW", ref_nmf.NMFD, (2, 21, 61), (21, 4, 5), (2, 4, 57), 2, 20, 0.5, None)
+    run_sfit("sfit_nmfd_kl_sH", ref_nmf.NMFD, (2, 21, 61), (21, 4, 5), (2, 4, 57), 1, 20, None, 0.4)
+    run_sfit("sfit_nmf2d_both", ref_nmf.NMF2D, (1, 6, 20, 30), (6, 3, 3, 4), (1, 3, 18, 27), 2, 15, 0.5, 0.4)
+
+    # --- trainer.SparsityProj (trainer.py:124-190): steps on one NMF module, closure = beta_div of its reconstruction ---
+    # (short runs: once the loss flattens, `loss <= init_loss` is decided by rounding and the step sizes of two
+    # implementations part ways)
+    # lr0 = 1 is the optimizer's default (the first steps walk through the halving branch); the others start from a step
+    # size a user would set for this problem
+    for name, which, beta, sp, steps, lr0 in (("sproj_W", "W", 2, 0.5, 4, 1.0), ("sproj_WH", "WH", 2, 0.4, 5, 1e-3),
+                                              ("sproj_H_kl", "H", 1, 0.6, 2, 1e-5)):
+        V, W0, H0 = make_inputs((N, C), (C, R), (N, R))
+        m = ref_nmf.NMF(W=W0, H=H0)
+        params = [getattr(m, a) for a in which]
+        tr = ref_trainer.SparsityProj(params, sp)
+        tr.param_groups[0]["lr"] = lr0
+
+        def closure():
+            tr.zero_grad()
+            return ref_beta_div(m(), V, beta)
+        losses = [float(tr.step(closure)) for _ in range(steps)]
+        put(name, dict(V=V, W0=W0, H0=H0, W=m.W, H=m.H, losses=torch.tensor(losses, dtype=torch.float64)),
+            dict(beta=beta, sparsity=sp, steps=steps, lr0=lr0, lr=tr.param_groups[0]["lr"], on_W=int("W" in which), on_H=int("H" in which)))
+    np.savez_compressed(os.path.join(GOLD, "reference_hoyer.npz"), **flat)
+    print(f"wrote reference_hoyer.npz ({os.path.getsize(os.path.join(GOLD, 'reference_hoyer.npz')) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg2", action="store_true")
@@ -408,9 +491,13 @@ if __name__ == "__main__":
     ap.add_argument("--next-rows", action="store_true", help="only the BetaMu / PLCA fixtures (reference_next.npz)")
     ap.add_argument("--plca", action="store_true", help="only the SIPLCA / SIPLCA2 / SIPLCA3 fixtures (reference_plca.npz)")
     ap.add_argument("--sparse", action="store_true", help="only the sparse-target fixtures (reference_sparse.npz)")
+    ap.add_argument("--hoyer", action="store_true", help="only the _proj_func / sparse_fit / SparsityProj fixtures (reference_hoyer.npz)")
     ap.add_argument("--nd", action="store_true", help="only the NMF2D / NMF3D fixtures (reference_nd.npz)")
     a = ap.parse_args()
     print("reference:", torchnmf.__file__, torchnmf.__version__, "torch", torch.__version__)
+    if a.hoyer:
+        hoyer_cases()
+        sys.exit(0)
     if a.plca:
         plca_cases()
         sys.exit(0)

@@ -786,4 +786,13 @@ int nmfb200_nmfd_loss(nmfb200_ctx* ctx, const float* W, const float* H, double b
                         loss_dev, (cudaStream_t)stream);
 }
 
+int nmfb200_hoyer_project(int device, float* x, int64_t outer, int64_t D, int64_t inner, const float* k1, const float* k2,
+                          void* zeroed_ws, void* stream) {
+  if (!x || !k1 || !k2 || !zeroed_ws) return fail(NMFB200_ERR_INVALID, "null pointer");
+  if (outer < 1 || inner < 1 || D < 1 || D > 0x7fffffff) return fail(NMFB200_ERR_INVALID, "bad shape");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(NMFB200_ERR_CUDA, "cannot select the device");
+  return hoyer_project(x, outer, (int)D, inner, k1, k2, (unsigned char*)zeroed_ws, (cudaStream_t)stream);
+}
+
 }  // extern "C"

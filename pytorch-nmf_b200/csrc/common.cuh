@@ -95,6 +95,12 @@ int matrix_minmax(const float* V, int64_t rows, int64_t cols, int64_t ld, float*
 // *out = sum of n doubles in fixed order (single block)
 int sum_partials(const double* p, int n, double* out, cudaStream_t st);
 
+// project.cu -------------------------------------------------------------------------------
+// Hoyer's projection (nmf.py:21-49) of every slice x[:, j, :] of x viewed as (outer, D, inner) onto {v >= 0, |v|_1 = k1[j],
+// |v|_2^2 = k2[j]}, in place; zeroed_ws: D * outer * inner bytes of scratch.
+int hoyer_project(float* x, int64_t outer, int D, int64_t inner, const float* k1, const float* k2,
+                  unsigned char* zeroed_ws, cudaStream_t st);
+
 // sparse_nmf.cu ----------------------------------------------------------------------------
 // Sparse-target NMF for beta 1 and 2 (nmf.py:603-638): update terms at the non-zeros of V only, one warp per compressed segment.
 int sparse_numerator(const int64_t* ptr, const int64_t* idx, const float* val, const float* Fself, const float* Fother,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nmfb200_nmfd_raw_terms_numel": (_i64, [_vp, _int, _dbl]),
     "nmfb200_nmfd_raw_terms": (_int, [_vp, _vp, _vp, _int, _dbl, _vp, _vp]),
     "nmfb200_nmfd_sync_factors": (_int, [_vp]),
+    "nmfb200_hoyer_project": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

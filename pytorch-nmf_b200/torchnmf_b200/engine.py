@@ -67,6 +67,32 @@ def cached_workspace_bytes():
 
 
 
+def hoyer_project_(x, dim, k1, k2):
+    """Project every slice of `x` along `dim` onto {v >= 0, |v|_1 = k1[j], |v|_2^2 = k2[j]} IN PLACE: ONE launch of
+    `nmfb200_hoyer_project` (include/nmf_b200.h) for what the reference does with a Python loop over the slices around
+    `_proj_func` (nmf.py:21-49, :519-522; trainer.py:176-181).  x: contiguous fp32 CUDA tensor; k1 / k2: sequences or
+    tensors of x.shape[dim] values (device tensors are used as they are: no host synchronisation)."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise TypeError("hoyer_project_: x must be a CUDA tensor (the library has no CPU path)")
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("hoyer_project_: x must be a contiguous float32 tensor")
+    D = x.shape[dim]
+    outer = 1
+    for n in x.shape[:dim]:
+        outer *= n
+    inner = x.numel() // max(outer * D, 1)
+    if x.numel() == 0:
+        return x
+    k1 = torch.as_tensor(k1, dtype=torch.float32, device=x.device).contiguous()
+    k2 = torch.as_tensor(k2, dtype=torch.float32, device=x.device).contiguous()
+    assert k1.numel() == D and k2.numel() == D
+    zeroed = torch.empty(x.numel(), dtype=torch.uint8, device=x.device)
+    lib = _capi.load()
+    _capi.check(lib.nmfb200_hoyer_project(x.device.index if x.device.index is not None else torch.cuda.current_device(),
+                                          _ptr(x), outer, D, inner, _ptr(k1), _ptr(k2), _ptr(zeroed), _stream(x.device)))
+    return x
+
+
 def release_workspaces():
     """Free every cached engine workspace (device memory held between fit() calls)."""
     lib = _capi.load()
@@ -135,6 +161,22 @@ class _CudaEngine:
     def check_health(self):
         """Raise if a kernel of the library aborted an internal wait since the last check (synchronises)."""
         _capi.check(self._lib.nmfb200_ctx_check_health(self._ctx, _stream(self.device)))
+
+    # ---- what sparse_fit (nmf.py:411-599) needs beyond the MU updates ----
+    def project(self, x, dim, k1, k2):
+        """Hoyer projection of every slice of x along `dim`, in place (one launch)."""
+        return hoyer_project_(x, dim, k1, k2)
+
+    def loss_at(self, W, H, beta):
+        """beta-divergence of the reconstruction from TRIAL factors (same shapes as the engine's own; a line search's
+        candidate).  The engine's operand copies follow the trial factors: call sync() after committing or discarding."""
+        keep = self.W, self.H
+        self.W, self.H = W, H
+        try:
+            self.sync()
+            return self.loss(beta)
+        finally:
+            self.W, self.H = keep
 
 
 class CudaNmfEngine(_CudaEngine):

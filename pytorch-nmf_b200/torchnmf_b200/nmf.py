@@ -13,8 +13,10 @@ device, runs there, and copies the factors back into the same Parameter storages
 mode, the `e2e` number of bench.py).  Without a CUDA device or without the built library it raises.
 
 `NMF2D` (:782-865) and `NMF3D` (:868-942) run the NMFD contractions with the last axis sliding and the outer axes as loops.
-Sparse targets are accepted by `NMF` and densified on the device (no SDDMM kernel).  Out of scope:
-`sparse_fit`.  `trainer.BetaMu` and `plca.PLCA` live in their own modules.
+Sparse targets are accepted by `NMF` (beta 1 / 2: the library's sparse kernels; other beta: densified on the device).
+`sparse_fit` (:411-599, Hoyer's sparseness-constrained projected gradient) runs on the same engine: gradients from the fused
+raw-terms launch, line-search losses from the fused loss launch, every component projected by ONE
+`nmfb200_hoyer_project` launch.  `trainer.BetaMu` / `SparsityProj` and `plca.*` live in their own modules.
 """
 import math
 import weakref
@@ -43,6 +45,34 @@ def _gamma(beta):
     if beta > 2:
         return 1.0 / (beta - 1.0)
     return 1.0
+
+
+def _get_norm(x, axis=1):
+    """L2 norm over every axis but `axis` (nmf.py:134-139)."""
+    dims = [d for d in range(x.dim()) if d != axis]
+    return (x * x).sum(dims).sqrt()
+
+
+@torch.no_grad()
+def _renorm(W, H, unit_norm="W"):
+    """Move the component norms to the other factor, in place (nmf.py:142-159)."""
+    if unit_norm == "W":
+        unit, other = W, H
+    elif unit_norm == "H":
+        unit, other = H, W
+    else:
+        raise ValueError("Input type isn't valid!")
+    n = _get_norm(unit)
+    unit /= n[(slice(None),) + (None,) * (unit.dim() - 2)]
+    other *= n[(slice(None),) + (None,) * (other.dim() - 2)]
+
+
+def _proj_func(s, k1, k2):
+    """Hoyer's projection of ONE vector (any shape) onto {v >= 0, |v|_1 = k1, |v|_2^2 = k2} (nmf.py:21-49); returns a new
+    tensor.  Runs in the library (`nmfb200_hoyer_project`): CUDA tensors only."""
+    out = s.detach().clone().reshape(1, 1, -1)
+    _engine.hoyer_project_(out, 1, [float(k1)], [float(k2)])
+    return out.view(s.shape)
 
 
 class _NullBar:
@@ -133,23 +163,10 @@ class BaseComponent(torch.nn.Module):
     _sparse_targets = False       # NMF only (nmf.py:603-638); the convolutive models raise, as in the reference
     _sparse_kernels = True        # beta 1 / 2 on a sparse target: the library's sparse kernels (False: densify)
 
-    @torch.no_grad()
-    def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
-            precision="auto", group=None):
-        """Learn the model for `V` by minimising the beta-divergence with multiplicative updates.
-
-        Positional arguments, defaults, return value (`n_iter`) and exceptions are those of
-        `BaseComponent.fit` in the reference (nmf.py:298-409).  Keyword-only extras:
-
-        precision: "auto" | "f32" | "f16" | "f16_split" -- arithmetic of the contraction kernels ("auto": fp16
-                   tensor-core operands where the target fits their range, fp32 CUDA cores otherwise)
-        group:     a torch.distributed process group; V and H are then this rank's ROW shard
-                   (rows of V <-> rows of H) and W is replicated; one all-reduce per W update.
-
-        dtype: the kernels keep fp32 master factors and fp32 accumulators.  The reference computes in the module's
-        dtype (nmf.py:214-218); here a float64 / half module (or target) is staged through fp32 copies and the result
-        is written back into the same Parameter storages in their own dtype.
-        """
+    def _open_engine(self, V, beta, precision, group, sparse_kernels):
+        """Shared entry of `fit` / `sparse_fit`: validation that needs no device pass, placement of V / W / H on the CUDA
+        device (host buffers and other dtypes are staged through fp32 device copies) and the engine for this target.
+        Returns (engine, W, H, Wd, Hd, staged): W / H the Parameters, Wd / Hd the fp32 device tensors the engine updates."""
         sparse_target = V.is_sparse
         if sparse_target and not self._sparse_targets:
             raise NotImplementedError                      # nmf.py:294-295: only NMF derives the sparse update
@@ -177,7 +194,8 @@ class BaseComponent(torch.nn.Module):
             on_gpu = W.device.type == "cuda"
             dev = W.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
             Vd = V.to(dev, non_blocking=True)
-            use_sparse_kernels = (sparse_target and beta in (1, 2) and group is None and self._sparse_kernels)
+            use_sparse_kernels = (sparse_kernels and sparse_target and beta in (1, 2) and group is None
+                                  and self._sparse_kernels)
             if not use_sparse_kernels:
                 Vd = (Vd.to_dense() if sparse_target else Vd).to(f32).contiguous()
             if on_gpu and W.dtype == f32 and H.dtype == f32:
@@ -191,11 +209,32 @@ class BaseComponent(torch.nn.Module):
             eng = (_engine.CudaSparseNmfEngine(Vd.coalesce(), Wd, Hd) if use_sparse_kernels
                    else self._build_engine(Vd, Wd, Hd, precision))
         else:
-            eng = self._engine_factory(V, W.data, H.data)
+            Wd, Hd = W.data, H.data
+            eng = self._engine_factory(V, Wd, Hd)
         if group is not None:
             if eng.kind != "nmf":
                 raise NotImplementedError("row sharding is implemented for NMF only (NMFD: replicas only)")
             eng = _engine.ShardedEngine(eng, group)
+        return eng, W, H, Wd, Hd, staged
+
+    @torch.no_grad()
+    def fit(self, V, beta=1, tol=1e-4, max_iter=200, verbose=False, alpha=0, l1_ratio=0, *,
+            precision="auto", group=None):
+        """Learn the model for `V` by minimising the beta-divergence with multiplicative updates.
+
+        Positional arguments, defaults, return value (`n_iter`) and exceptions are those of
+        `BaseComponent.fit` in the reference (nmf.py:298-409).  Keyword-only extras:
+
+        precision: "auto" | "f32" | "f16" | "f16_split" -- arithmetic of the contraction kernels ("auto": fp16
+                   tensor-core operands where the target fits their range, fp32 CUDA cores otherwise)
+        group:     a torch.distributed process group; V and H are then this rank's ROW shard
+                   (rows of V <-> rows of H) and W is replicated; one all-reduce per W update.
+
+        dtype: the kernels keep fp32 master factors and fp32 accumulators.  The reference computes in the module's
+        dtype (nmf.py:214-218); here a float64 / half module (or target) is staged through fp32 copies and the result
+        is written back into the same Parameter storages in their own dtype.
+        """
+        eng, W, H, Wd, Hd, staged = self._open_engine(V, beta, precision, group, sparse_kernels=True)
 
         try:
             vmin, vmax = eng.minmax()
@@ -252,6 +291,97 @@ class BaseComponent(torch.nn.Module):
         finally:
             eng.close()
         return n_iter + 1                                                                  # nmf.py:409
+
+
+    @torch.no_grad()
+    def sparse_fit(self, V, beta=2, max_iter=200, verbose=False, sW=None, sH=None, *, precision="auto"):
+        """Learn the model for `V` under Hoyer's sparseness constraints (reference: nmf.py:411-599).
+
+        Positional arguments, defaults, return value and exceptions are the reference's: `sW` / `sH` in (0, 1) fix the
+        sparseness of every component W[:, r] / H[:, r]; a factor without a constraint takes the multiplicative update
+        (nmf.py:503-511), a constrained one a projected-gradient step with a halving line search (:513-538), and H is
+        re-normalised to unit component norms after its update (:588).  No stop rule: `max_iter` iterations are run.
+
+        On the engine: the gradient is `positive - negative` of ONE fused raw-terms launch (`nmfb200_*_raw_terms`), every
+        line-search loss one fused loss launch on the trial factor, and the per-component Python loop around `_proj_func`
+        (nmf.py:519-522: R x rounds x 7 ATen launches and one `.item()` per round) is one `nmfb200_hoyer_project` launch.
+
+        precision: as in `fit`; "auto" resolves to "f32" when a constraint is active (the line search compares losses of
+        nearly equal trial points).  Sparse targets are densified on the device.
+        """
+        constrained = ((sW is not None and self.W is not None and self.W.requires_grad)
+                       or (sH is not None and self.H is not None and self.H.requires_grad))
+        if precision == "auto" and constrained:
+            precision = "f32"
+        eng, W, H, Wd, Hd, staged = self._open_engine(V, beta, precision, None, sparse_kernels=False)
+        try:
+            vmin, vmax = eng.minmax()
+            assert vmin >= 0., "Target should be non-negative."                            # nmf.py:447-448
+            if vmin == 0 and beta <= 0:                                                    # nmf.py:450-454
+                raise ValueError("When beta <= 0 and V contains zeros, the training process may diverge. "
+                                 "Please add small values to V, or use a positive beta value.")
+            train_w, train_h = W.requires_grad, H.requires_grad
+            R = Wd.shape[1]
+            L1a = L1s = None
+            if sW is not None and train_w:                                                 # nmf.py:459-467
+                L1a = Wd[:, 0].numel() ** 0.5 * (1 - sW) + sW
+                eng.project(Wd, 1, [L1a] * R, [1.0] * R)
+            if sH is not None and train_h:                                                 # nmf.py:469-477
+                L1s = Hd[:, 0].numel() ** 0.5 * (1 - sH) + sH
+                eng.project(Hd, 1, [L1s] * R, [1.0] * R)
+            eng.sync()
+            gamma = _gamma(beta)                                                           # nmf.py:479-484
+            step = {0: 1.0, 1: 1.0}                                                        # nmf.py:490
+
+            def projected_step(which, L1):
+                """nmf.py:513-538 (W) / :559-586 (H): gradient step, projection of every component, halving line search."""
+                cur = Wd if which == 0 else Hd
+                loss = eng.loss(beta)
+                num, den = eng.raw_terms(which, beta)
+                if beta == 1:
+                    den = den.view((1, -1) + (1,) * (cur.dim() - 2))                       # colsum of the other factor
+                grad = den - num
+                for _ in range(10):
+                    new = cur - step[which] * grad
+                    norms = _get_norm(new)
+                    eng.project(new, 1, L1 * norms, norms * norms)
+                    new_loss = eng.loss_at(new if which == 0 else Wd, Hd if which == 0 else new, beta)
+                    if new_loss <= loss:
+                        break
+                    step[which] *= 0.5
+                step[which] *= 1.2
+                cur.copy_(new)
+                eng.sync()
+
+            bar = _tqdm(total=max_iter, disable=not verbose) if _tqdm is not None else _NullBar()
+            n_iter = -1
+            with bar as pbar:
+                for n_iter in range(max_iter):
+                    if train_w:
+                        if L1a is None:
+                            eng.update_w(beta, gamma, 0.0, 0.0)                            # nmf.py:503-511
+                        else:
+                            projected_step(0, L1a)
+                    if train_h:
+                        if L1s is None:
+                            eng.update_h(beta, gamma, 0.0, 0.0)                            # nmf.py:549-557
+                        else:
+                            projected_step(1, L1s)
+                        _renorm(Wd, Hd, "H")                                               # nmf.py:588
+                        eng.sync()
+                    if n_iter % 10 == 9 and verbose:                                       # nmf.py:590-598 (display only)
+                        d = eng.loss(beta)
+                        pbar.set_postfix(loss=math.sqrt(2.0 * d) if d >= 0 else float("nan"))
+                        pbar.update(10)
+            if hasattr(eng, "check_health"):
+                eng.check_health()
+            if staged:
+                W.data.copy_(Wd)
+                H.data.copy_(Hd)
+            self.last_fit_precision = eng.precision_for(beta) if hasattr(eng, "precision_for") else eng.precision
+        finally:
+            eng.close()
+        return n_iter + 1                                                                  # nmf.py:599
 
 
 class NMF(BaseComponent):

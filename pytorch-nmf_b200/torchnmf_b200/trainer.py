@@ -17,6 +17,11 @@ Two ways to obtain the two gradient terms `neg = relu(d<WH, V (WH+eps)^(beta-2)>
   return the module itself instead of its output (`return V, model`) to skip the forward pass as well.  The
   convolutive modules (`NMFD`, `NMF2D`, `NMF3D`) take the same route through `nmfb200_nmfd_raw_terms` (the sliding
   contractions of csrc/nmfd.cu / csrc/tc_nmfd.cu instead of two passes through cuDNN's convolution backward).
+
+`SparsityProj` (trainer.py:124-190): Hoyer's projected-gradient step around a loss closure.  The gradient is the
+closure's own (autograd); the projection of every slice of every parameter -- in the reference a Python loop over the
+slices around the TorchScript `_proj_func`, one host synchronisation per round and slice -- is one
+`nmfb200_hoyer_project` launch per parameter.
 """
 import weakref
 
@@ -26,7 +31,7 @@ from torch.optim.optimizer import Optimizer
 from .constants import eps
 from . import engine as _engine
 
-__all__ = ["BetaMu"]
+__all__ = ["BetaMu", "SparsityProj"]
 
 
 def _gamma(beta):
@@ -185,3 +190,67 @@ def _source_module(WH):
     """The NMF module whose plain reconstruction `WH` is (tagged by `NMF.forward`), else None."""
     ref = getattr(WH, "_nmf_b200_src", None)
     return ref() if isinstance(ref, weakref.ref) else None
+
+
+def _get_norm(x, axis=1):
+    """nmf.py:134-139."""
+    dims = [d for d in range(x.dim()) if d != axis]
+    return (x * x).sum(dims).sqrt()
+
+
+def _project_slices_(p, dim, k1, k2):
+    """Every slice of `p` along `dim` <- its Hoyer projection (nmf.py:21-49), in place, in the library.  A parameter that
+    is not a contiguous fp32 CUDA tensor is staged through one (host buffers: through the current CUDA device, like `fit`)."""
+    if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous():
+        _engine.hoyer_project_(p, dim, k1, k2)
+        return
+    if not (p.is_cuda or torch.cuda.is_available()):
+        raise RuntimeError("SparsityProj needs a CUDA device (sm_100a) for the projection; there is no CPU fallback")
+    dev = p.device if p.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    tmp = p.detach().to(dev, torch.float32).contiguous()
+    _engine.hoyer_project_(tmp, dim, torch.as_tensor(k1).to(dev), torch.as_tensor(k2).to(dev))
+    p.copy_(tmp)
+
+
+class SparsityProj(Optimizer):
+    """Sparseness-constrained gradient projection (Hoyer 2004; reference: trainer.py:124-147).
+
+    Arguments:
+        params: iterable of parameters or dicts defining parameter groups
+        sparsity: the target sparseness of every slice of every parameter, 0 < sparsity < 1
+        dim: the axis whose slices are the constrained vectors.  Default: 1
+        max_iter: maximal number of loss evaluations per step.  Default: 10
+    """
+
+    def __init__(self, params, sparsity, dim=1, max_iter=10):
+        if not 0.0 < sparsity < 1.:
+            raise ValueError("Invalid sparsity value: {}".format(sparsity))
+        super().__init__(params, dict(sparsity=sparsity, lr=1, dim=dim, max_iter=max_iter))
+
+    @torch.no_grad()
+    def step(self, closure):
+        """One projected-gradient step per parameter group with a halving line search (trainer.py:150-190).
+        `closure()` re-evaluates the model and returns the loss."""
+        loss = None
+        for group in self.param_groups:
+            sparsity, lr, dim, max_iter = group["sparsity"], group["lr"], group["dim"], group["max_iter"]
+            with torch.enable_grad():
+                init_loss = closure()
+                init_loss.backward()
+            params = [(p, p.grad.clone()) for p in group["params"] if p.grad is not None]
+            for _ in range(max_iter):
+                for p, g in params:
+                    norms = _get_norm(p, dim)                                  # trainer.py:173: of p BEFORE the step
+                    p.add_(g, alpha=-lr)
+                    n = p.numel() // p.shape[dim]
+                    L1 = n ** 0.5 * (1 - sparsity) + sparsity
+                    _project_slices_(p, dim, L1 * norms, norms * norms)        # trainer.py:176-181
+                loss = closure()
+                if loss <= init_loss:
+                    break
+                for p, g in params:
+                    p.add_(g, alpha=lr)                                        # trainer.py:186-187
+                lr *= 0.5
+            lr *= 1.2
+            group["lr"] = lr
+        return loss

@@ -5,6 +5,7 @@ exercised on a machine with no GPU (`-m "not gpu"`, gloo).  They are never impor
 """
 import torch
 
+from oracle import hoyer_oracle as hoy
 from oracle import mu_oracle as orc
 
 
@@ -30,10 +31,28 @@ class _OracleEngine:
     def loss(self, beta):
         return float(self.loss_tensor(beta))
 
+    # sparse_fit's extras (engine.py: project / loss_at / raw_terms)
+    def project(self, x, dim, k1, k2):
+        x.copy_(hoy.project_slices(x, dim, torch.as_tensor(k1), torch.as_tensor(k2)))
+        return x
+
+    def loss_at(self, W, H, beta):
+        return float(orc.beta_div(self._recon(H, W), self.V, beta))
+
+    def raw_terms(self, which, beta):
+        """(raw numerator, raw denominator) of one factor's update; the denominator is (R,) for beta == 1."""
+        Pn, Pp = orc.phi(self.V, self._recon(self.H, self.W), beta)
+        contract = (lambda G: self._grad_w(G, self.H, self.W)) if which == 0 else (lambda G: self._grad_h(G, self.W, self.H))
+        other = self.H if which == 0 else self.W
+        den = other.sum([d for d in range(other.dim()) if d != 1]) if beta == 1 else contract(Pp)
+        return contract(Pn), den
+
 
 class OracleNmfEngine(_OracleEngine):
     kind = "nmf"
     _recon = staticmethod(orc.nmf_reconstruct)
+    _grad_w = staticmethod(lambda G, H, W: G.t() @ H)
+    _grad_h = staticmethod(lambda G, W, H: G @ W)
 
     def update_w(self, beta, gamma, l1, l2):
         self.W.copy_(orc.nmf_update_w(self.V, self.W, self.H, beta, gamma, l1, l2))
@@ -56,6 +75,8 @@ class OracleNmfEngine(_OracleEngine):
 class OracleNmfdEngine(_OracleEngine):
     kind = "nmfd"
     _recon = staticmethod(orc.nmfd_reconstruct)
+    _grad_w = staticmethod(lambda G, H, W: orc.nmfd_grad_w(G, H, W.shape[2]))
+    _grad_h = staticmethod(lambda G, W, H: orc.nmfd_grad_h(G, W, H.shape[2]))
 
     def update_w(self, beta, gamma, l1, l2):
         self.W.copy_(orc.nmfd_update_w(self.V, self.W, self.H, beta, gamma, l1, l2))
