@@ -106,6 +106,14 @@ int nmfb200_nmf_iterate(nmfb200_ctx* ctx, float* W, float* H, double beta, doubl
  * (one element, overwritten).  Row shards add: the sum over ranks is the global divergence. */
 int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
                      double* loss_dev, void* stream);
+/* The same value, evaluated at the factors the NEXT W update starts from (nmf.py:393-402 runs right before nmf.py:367 of the
+ * following iteration): on the tensor-core path for beta == 1 the loss sums come out of the W update's own contraction pass
+ * (one lg2 per element on the S tile that pass forms anyway, instead of a pass over V of its own), and the next
+ * nmfb200_nmf_update_w / nmfb200_nmf_iterate on UNCHANGED factors with the same beta skips its contraction.  Any other
+ * call in between (or a stop of the fit) simply discards the prefetched numerators.  Elsewhere: identical to
+ * nmfb200_nmf_loss. */
+int nmfb200_nmf_loss_prefetch_w(nmfb200_ctx* ctx, const float* W, const float* H, double beta,
+                                double* loss_dev, void* stream);
 
 /* Row-sharded W update.  `partial` is a device fp32 buffer of
  * nmfb200_nmf_w_partial_numel() elements receiving this shard's raw numerator (C*R), then either

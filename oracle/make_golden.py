@@ -465,7 +465,7 @@ def hoyer_cases():
     # lr0 = 1 is the optimizer's default (the first steps walk through the halving branch); the others start from a step
     # size a user would set for this problem
     for name, which, beta, sp, steps, lr0 in (("sproj_W", "W", 2, 0.5, 4, 1.0), ("sproj_WH", "WH", 2, 0.4, 5, 1e-3),
-                                              ("sproj_H_kl", "H", 1, 0.6, 2, 1e-5)):
+                                              ("sproj_H", "H", 2, 0.6, 4, 1e-3)):
         V, W0, H0 = make_inputs((N, C), (C, R), (N, R))
         m = ref_nmf.NMF(W=W0, H=H0)
         params = [getattr(m, a) for a in which]

@@ -442,6 +442,16 @@ int nmfb200_nmf_loss(nmfb200_ctx* ctx, const float* W, const float* H, double be
                        ctx->loss_max_blocks, loss_dev, st);
 }
 
+int nmfb200_nmf_loss_prefetch_w(nmfb200_ctx* ctx, const float* W, const float* H, double beta, double* loss_dev,
+                                void* stream) {
+  CTX_GUARD(ctx, 0);
+  if (!ctx->has_target) return fail(NMFB200_ERR_STATE, "set_target has not been called");
+  if (!W || !H || !loss_dev) return fail(NMFB200_ERR_INVALID, "null pointer");
+  if (!ctx->sparse && use_tc(ctx, beta) && tc_supports_loss(ctx->tc, beta))
+    return tc_loss_prefetch_w(ctx->tc, W, H, beta, loss_dev, (cudaStream_t)stream);
+  return nmfb200_nmf_loss(ctx, W, H, beta, loss_dev, stream);
+}
+
 int64_t nmfb200_nmf_w_partial_numel(const nmfb200_ctx* ctx, double beta) {
   if (!ctx || ctx->kind != 0) return -1;
   return beta == 1.0 ? ctx->C * ctx->R + ctx->R : 2 * ctx->C * ctx->R;

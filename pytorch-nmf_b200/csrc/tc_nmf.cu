@@ -115,7 +115,10 @@ struct SmemLayout {
 // tensor cores' truncation bias).
 enum : int { kBmKL = 0, kBmIS = 1, kBm05 = 2, kBm15 = 3, kBmGen = 4, kBmEU = 5 };
 
-template <class C, int BM, bool LOSS>
+// FOLD (beta 1 update kernels only): the W update's contraction ALSO accumulates the loss sums of the LOSS kernel from the S
+// tile it forms anyway (metrics.py:22 needs sum V lg(WH + eps) and sum WH at exactly the factors the next W update starts
+// from), so the loss evaluation of every 10th iteration costs one lg2 per element instead of a pass over V of its own.
+template <class C, int BM, bool LOSS, bool FOLD = false>
 __global__ void __launch_bounds__(C::kThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmG,
                    const __grid_constant__ CUtensorMap tmV, const TcKernelParams p) {
@@ -146,6 +149,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   static_assert(!TWO || (!SPLIT && RP == 64 && TN == 128 && NS == 2), "two-output kernels: fast mode, R <= 64");
   static_assert(TN == 64 || TN == 128, "tile width");
   static_assert(RP == 64 || RP == 128, "padded rank");
+  static_assert(!FOLD || (!LOSS && BM == kBmKL), "loss folded into the update kernel: beta 1 only");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw32 = ptx::smem_u32(smem_raw);
   const uint32_t sbase = (raw32 + 1023u) & ~1023u;
@@ -432,6 +436,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       }
       const uint64_t C1 = ptx::pk2(c1, c1), C2 = ptx::pk2(c2, c2), NEGPC = ptx::pk2(negpc, negpc), Z2 = ptx::pk2(0.f, 0.f);
       const uint64_t EUCV = ptx::pk2(eu_cv, eu_cv), EUNCS = ptx::pk2(-eu_cs, -eu_cs);
+      // FOLD: x = WH + eps in true scale (the LOSS kernel's c1 / c2), sum v~ lg2 x and sum S~ of this thread and tile
+      const float c1l = exp2f((float)(-ea - eb));
+      const uint64_t C1L = ptx::pk2(c1l, c1l), C2L = ptx::pk2(kEps, kEps), ONE2 = ptx::pk2(1.f, 1.f);
+      float fold_a = 0.f;
+      uint64_t FOLD_B = Z2;
       // this thread's row inside a 128-byte-swizzled V sub-tile: byte (row, 16-byte chunk k) sits at row*128 + ((k ^ row%8) << 4)
       const uint32_t vrow = (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4);
       const uint32_t tS0 = tmem + lane_addr + kColS;            // TMEM address of this warp's lanes, stage 0, column 0
@@ -466,6 +475,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             Pb = ptx::fma2(Sb, EUNCS, ptx::fma2(Vb, EUCV, Z2));
           } else {
             const uint64_t Xa = ptx::fma2(Sa, C1, C2), Xb = ptx::fma2(Sb, C1, C2);   // (WH + eps) in the scale of V~ / P~
+            if constexpr (FOLD) {                                                    // metrics.py:22 on the same S tile
+              float l0, l1, l2, l3;
+              ptx::upk2(ptx::fma2(Sa, C1L, C2L), l0, l1);
+              ptx::upk2(ptx::fma2(Sb, C1L, C2L), l2, l3);
+              fold_a = fmaf(va.x, __log2f(l0), fold_a);
+              fold_a = fmaf(va.y, __log2f(l1), fold_a);
+              fold_a = fmaf(vb.x, __log2f(l2), fold_a);
+              fold_a = fmaf(vb.y, __log2f(l3), fold_a);
+              FOLD_B = ptx::fma2(Sa, ONE2, FOLD_B);
+              FOLD_B = ptx::fma2(Sb, ONE2, FOLD_B);
+            }
             uint64_t Ra, Rb;                                                         // 1 / x of pair a, pair b
             if ((qd & 3) != 0) {
               // batched: 1 / x0 = x2 r0, 1 / x1 = x3 r1, 1 / x2 = x0 r0, 1 / x3 = x1 r1 with r = rcp(x_a x_b)
@@ -568,6 +588,14 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         if (lane == 0 && g == NRW - 1 && q == 3) TC_TRACE(tt, 11);
         st = st1; phS = phS1; sv = sv1; phV = phV1; tS = tS1; vT = vT1;
         if (PSEP && ++pb == (uint32_t)NP) { pb = 0; phP ^= 1; }
+        if constexpr (FOLD) {                    // per-tile fp32 sums (TN / NRW elements per thread) into the double totals
+          float b0, b1;
+          ptx::upk2(FOLD_B, b0, b1);
+          accA += (double)fold_a;
+          accB += (double)(b0 + b1);
+          fold_a = 0.f;
+          FOLD_B = Z2;
+        }
       }
     } else {
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -699,7 +727,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       t += n;
     }
     }   // LOSS and two-output kernels
-    if (LOSS) {
+    if (LOSS || FOLD) {
       for (int o = 16; o > 0; o >>= 1) {
         accA += __shfl_xor_sync(0xffffffffu, accA, o);
         accB += __shfl_xor_sync(0xffffffffu, accB, o);
@@ -812,7 +840,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kCtl0 + 1) ptx::tmem_dealloc(tmem, kTmemCols);
-  if (LOSS && threadIdx.x == (kCtl0 + 3) * 32) {          // fixed-order sum of the 8 ratio warps
+  if ((LOSS || FOLD) && threadIdx.x == (kCtl0 + 3) * 32) {          // fixed-order sum of the 8 ratio warps
     double a = 0.0, b = 0.0;
     for (int w = 0; w < 4 * NRW; ++w) { a += loss_slots[2 * w]; b += loss_slots[2 * w + 1]; }
     p.loss_part[2 * blockIdx.x] = a;
@@ -1644,6 +1672,7 @@ struct TcState {
   double* vconst = nullptr;         // {sum V, sum V log(V+eps)}
   unsigned long long* vlossy = nullptr;   // positive target entries the scaled fp16 copy cannot hold at full precision
   double* loss_part = nullptr;      // [num_sms][2]
+  bool w_pending = false;           // tc_loss_prefetch_w: the W update's partial numerators of the CURRENT factors are in `part`
   const float* Vsrc = nullptr;      // the registered fp32 target (borrowed) for the V-only loss terms
   int64_t ldv = 0;
   double* vbeta = nullptr;          // device: V-only loss term of beta `vbeta_for`
@@ -1818,6 +1847,7 @@ bool tc_supports_loss(const TcState* s, double beta) { return tc_supports_beta(s
 bool tc_supports_partial(const TcState* s, double beta) { return beta != 2.0 && tc_supports_beta(s, beta); }
 
 int tc_set_target(TcState* s, const float* V, int64_t ldv, const float* minmax_dev, cudaStream_t st) {
+  s->w_pending = false;
   set_vexp_kernel<<<1, 32, 0, st>>>(minmax_dev, s->exps);
   NMF_LAUNCH_CHECK();
   dim3 grid((unsigned)ceil_div(s->C, 64), (unsigned)ceil_div(s->N, 64));
@@ -1961,11 +1991,12 @@ int ensure_synced(TcState* s, const float* W, const float* H, double beta, cudaS
   return 0;
 }
 
-template <class C, int BM, bool LOSS>
+template <class C, int BM, bool LOSS, bool FOLD = false>
 int launch_contract_t(TcState* s, int which, double beta, cudaStream_t st) {
   using L = SmemLayout<C::KW, C::TN, C::NF, C::NG, C::NV, C::NS, C::NP>;
   static_assert(L::kTotal + 1024 <= 232448, "shared memory budget (227 KB)");
-  auto kern = tc_contract_kernel<C, BM, LOSS>;
+  auto kern = tc_contract_kernel<C, BM, LOSS, FOLD>;
+  if (!LOSS) s->w_pending = false;       // every update contraction overwrites the partial numerators
   static unsigned long long attr_set_mask = 0;      // per device (one bit each): the attribute is per-device state
   const int smem = L::kTotal + 1024;     // slack so the kernel-visible base can be 1024-aligned
   if (!((attr_set_mask >> (s->device & 63)) & 1ull)) {
@@ -2036,6 +2067,15 @@ int launch_contract_one(TcState* s, int which, double beta, cudaStream_t st) {
   return launch_contract_t<CfgSplit128, BM, false>(s, which, beta, st);
 }
 
+// beta 1, W orientation, loss sums folded in (fast, non-split configurations)
+int launch_contract_w_fold(TcState* s, cudaStream_t st) {
+  if (s->Rp == 64) {
+    if (!s->psep) return launch_contract_t<CfgFast64A, kBmKL, false, true>(s, 0, 1.0, st);
+    return launch_contract_t<CfgFast64, kBmKL, false, true>(s, 0, 1.0, st);
+  }
+  return launch_contract_t<CfgFast128, kBmKL, false, true>(s, 0, 1.0, st);
+}
+
 template <int BM>
 int launch_loss_bm(TcState* s, double beta, cudaStream_t st) {
   if (s->Rp == 64) {
@@ -2068,10 +2108,15 @@ int launch_contract(TcState* s, int which, double beta, cudaStream_t st) {
 
 int tc_update_w(TcState* s, float* W, const float* H, double beta, double gamma, double l1, double l2,
                 cudaStream_t st) {
+  // tc_loss_prefetch_w already ran this contraction on these very factors (its numerators are still in `part`)
+  const bool reuse = s->w_pending && !s->dirty_w && !s->dirty_h && beta == 1.0;
+  s->w_pending = false;
   int rc = ensure_synced(s, W, H, beta, st);
   if (rc) return rc;
-  rc = launch_contract(s, 0, beta, st);
-  if (rc) return rc;
+  if (!reuse) {
+    rc = launch_contract(s, 0, beta, st);
+    if (rc) return rc;
+  }
   return apply_and_finish(s, 0, W, true, &s->plan_w, beta, gamma, l1, l2, st, nullptr, H);
 }
 
@@ -2112,6 +2157,7 @@ int tc_iterate(TcState* s, float* W, float* H, double beta, double gamma, double
   for (int i = 0; i < n_iter; ++i) {
     const int key = (int)((s->upd[0] & 1u) * 2u + (s->upd[1] & 1u));
     if (use_graph && s->gwarm && s->gexec[key]) {
+      s->w_pending = false;                          // the replayed iteration runs its own W contraction
       NMF_CUDA_CHECK(cudaGraphLaunch(s->gexec[key], st));
       s->upd[0]++; s->upd[1]++;
       count_launch(s->gkernels);
@@ -2305,6 +2351,24 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
     }
   }
   return rc;
+}
+
+bool tc_supports_loss_prefetch(const TcState* s, double beta) {
+  return beta == 1.0 && !s->split && s->trace == nullptr;
+}
+
+// The loss at the current factors from the W update's own contraction (beta 1): one pass over V yields both the loss sums and
+// the partial numerators; the next tc_update_w on unchanged factors skips its contraction.
+int tc_loss_prefetch_w(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {
+  if (!tc_supports_loss_prefetch(s, beta)) return tc_loss(s, W, H, beta, loss_dev, st);
+  int rc = ensure_synced(s, W, H, beta, st);
+  if (rc) return rc;
+  const int grid = launch_contract_w_fold(s, st);
+  if (grid <= 0) return 2;
+  tc_loss_final_kernel<<<1, 32, 0, st>>>(s->loss_part, grid, s->vconst, s->exps, loss_dev);
+  NMF_LAUNCH_CHECK();
+  s->w_pending = true;
+  return 0;
 }
 
 int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st) {

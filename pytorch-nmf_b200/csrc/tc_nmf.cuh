@@ -48,5 +48,8 @@ int tc_contract_only(TcState* s, const float* W, const float* H, int which, doub
 // debugging / health: report (and clear) a recorded mbarrier wait abort; synchronises the stream
 int tc_check_wait_abort(cudaStream_t st);
 int tc_loss(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st);
+// the same value out of the W update's own contraction pass (beta 1, non-split); the next tc_update_w on unchanged factors
+// reuses the partial numerators.  Falls back to tc_loss where the fold is not built.
+int tc_loss_prefetch_w(TcState* s, const float* W, const float* H, double beta, double* loss_dev, cudaStream_t st);
 
 }  // namespace nmfb200

@@ -36,6 +36,7 @@ SIGNATURES = {
     "nmfb200_nmf_update_h": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "nmfb200_nmf_iterate": (_int, [_vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _int, _vp]),
     "nmfb200_nmf_loss": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
+    "nmfb200_nmf_loss_prefetch_w": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
     "nmfb200_nmf_w_partial_numel": (_i64, [_vp, _dbl]),
     "nmfb200_nmf_w_partial": (_int, [_vp, _vp, _vp, _dbl, _vp, _vp]),
     "nmfb200_nmf_raw_terms_numel": (_i64, [_vp, _int, _dbl]),

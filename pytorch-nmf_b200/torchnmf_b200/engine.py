@@ -42,6 +42,9 @@ def _check_f32_cuda(t, name, device):
 # contexts.  release_workspaces() drops them all.
 _WORKSPACES = {}
 _MAX_WORKSPACES = 2
+# fit(): take every 10th iteration's loss out of the next W update's contraction pass where the library folds it
+# (nmfb200_nmf_loss_prefetch_w).  NMFB200_LOSS_FOLD=0: always the loss pass of its own (A/B timing).
+LOSS_FOLD = os.environ.get("NMFB200_LOSS_FOLD", "1") != "0"
 _CACHE_BYTES = int(float(os.environ.get("NMFB200_WORKSPACE_CACHE_MB", "8192")) * (1 << 20))
 
 
@@ -220,6 +223,15 @@ class CudaNmfEngine(_CudaEngine):
         _capi.check(self._lib.nmfb200_nmf_loss(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
                                                _stream(self.device)))
         return self._loss
+
+    def loss_prefetch_w(self, beta):
+        """The loss at the current factors, taken out of the NEXT W update's contraction pass where the library can fold it
+        (beta 1 on the tensor-core path): that update then skips its contraction.  Same value as loss() (synchronises)."""
+        _capi.check(self._lib.nmfb200_nmf_loss_prefetch_w(self._ctx, _ptr(self.W), _ptr(self.H), beta, _ptr(self._loss),
+                                                          _stream(self.device)))
+        val = float(self._loss.item())
+        self.check_health()
+        return val
 
     def contract_only(self, which, beta):
         """bench.py: launch only the fused contraction kernel (0 = W update's, 1 = H update's)."""

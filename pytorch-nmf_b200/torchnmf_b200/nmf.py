@@ -246,8 +246,11 @@ class BaseComponent(torch.nn.Module):
             l1_reg = alpha * l1_ratio                                                      # nmf.py:348
             l2_reg = alpha * (1 - l1_ratio)                                                # nmf.py:349
 
-            def fit_loss():
-                d = eng.loss(beta)
+            def fit_loss(more=False):
+                # `more`: a W update follows on these very factors -- the engine may take the loss out of that update's own
+                # contraction pass (engine.loss_prefetch_w) instead of a pass over V of its own
+                fold = more and _engine.LOSS_FOLD and hasattr(eng, "loss_prefetch_w")
+                d = eng.loss_prefetch_w(beta) if fold else eng.loss(beta)
                 return math.sqrt(2.0 * d) if d >= 0 else float("nan")                      # nmf.py:362,402
 
             loss_init = fit_loss()
@@ -263,7 +266,7 @@ class BaseComponent(torch.nn.Module):
                     eng.iterate(k, beta, gamma, l1_reg, l2_reg)                            # nmf.py:366-391, k times
                     n_iter += k
                     if n_iter % 10 == 9:                                                   # nmf.py:393
-                        loss = fit_loss()
+                        loss = fit_loss(more=n_iter + 1 < max_iter)
                         pbar.set_postfix(loss=loss)
                         pbar.update(10)
                         if (previous_loss - loss) / loss_init < tol:                       # nmf.py:405
@@ -275,7 +278,7 @@ class BaseComponent(torch.nn.Module):
                     if train_h:
                         eng.update_h(beta, gamma, l1_reg, l2_reg)                          # nmf.py:380-391
                     if n_iter % 10 == 9:                                                   # nmf.py:393
-                        loss = fit_loss()
+                        loss = fit_loss(more=train_w and group is None and n_iter + 1 < max_iter)
                         pbar.set_postfix(loss=loss)
                         pbar.update(10)
                         if (previous_loss - loss) / loss_init < tol:                       # nmf.py:405

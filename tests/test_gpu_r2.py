@@ -134,3 +134,85 @@ def test_nmfd_tensor_core_fit_is_bitwise_repeatable():
         outs.append((m.W.data.clone(), m.H.data.clone()))
     for W, H in outs[1:]:
         assert torch.equal(W, outs[0][0]) and torch.equal(H, outs[0][1])
+
+
+# ---- the loss folded into the W update's contraction pass (nmfb200_nmf_loss_prefetch_w) -----------------------------------
+def _kl_engine(N, C, R):
+    from torchnmf_b200 import engine as _engine
+    V, W0, H0 = _inputs((N, C), (C, R), (N, R))
+    W, H = W0.cuda(), H0.cuda()
+    return _engine.CudaNmfEngine(V.cuda(), W, H, "f16"), W, H
+
+
+@pytest.mark.parametrize("shape", [(1000, 777, 64), (640, 512, 128), (300, 260, 40)])
+def test_prefetched_loss_equals_the_loss_pass_and_feeds_the_next_w_update(shape):
+    """The fold computes the LOSS kernel's sums from the W contraction's own S tiles: same value (summation order aside), and
+    the W update that follows, which skips its contraction, gives the bits of a plain W update."""
+    N, C, R = shape
+    eng, W, H = _kl_engine(N, C, R)
+    try:
+        for _ in range(3):
+            eng.update_w(1.0, 1.0, 0.0, 0.0)
+            eng.update_h(1.0, 1.0, 0.0, 0.0)
+        want = eng.loss(1.0)
+        W_before = W.clone()
+        eng.update_w(1.0, 1.0, 0.0, 0.0)
+        W_plain = W.clone()
+        W.copy_(W_before)
+        eng.sync()
+        got = eng.loss_prefetch_w(1.0)
+        assert got == pytest.approx(want, rel=2e-6)
+        eng.update_w(1.0, 1.0, 0.0, 0.0)                    # reuses the prefetched numerators
+        assert torch.equal(W, W_plain)
+        # a prefetch that is NOT followed by the W update is dropped: H update, then a fresh W update
+        W.copy_(W_before)
+        eng.sync()
+        eng.update_h(1.0, 1.0, 0.0, 0.0)
+        eng.update_w(1.0, 1.0, 0.0, 0.0)
+        W_seq = W.clone()
+        H_seq = H.clone()
+    finally:
+        eng.close()
+    eng2, W2, H2 = _kl_engine(N, C, R)
+    try:
+        for _ in range(3):
+            eng2.update_w(1.0, 1.0, 0.0, 0.0)
+            eng2.update_h(1.0, 1.0, 0.0, 0.0)
+        eng2.loss_prefetch_w(1.0)
+        eng2.update_h(1.0, 1.0, 0.0, 0.0)                   # overwrites the partial numerators: the prefetch must not be used
+        eng2.update_w(1.0, 1.0, 0.0, 0.0)
+    finally:
+        eng2.close()
+    # eng ran one extra H update before this point (the one inside the loop body above is shared): compare like with like
+    eng3, W3, H3 = _kl_engine(N, C, R)
+    try:
+        for _ in range(3):
+            eng3.update_w(1.0, 1.0, 0.0, 0.0)
+            eng3.update_h(1.0, 1.0, 0.0, 0.0)
+        eng3.update_h(1.0, 1.0, 0.0, 0.0)
+        eng3.update_w(1.0, 1.0, 0.0, 0.0)
+    finally:
+        eng3.close()
+    assert torch.equal(W2, W3) and torch.equal(H2, H3)
+    assert torch.equal(W_seq, W3) and torch.equal(H_seq, H3)
+
+
+def test_fit_with_the_folded_loss_is_the_fit_with_the_loss_pass(monkeypatch):
+    """Same factors, same losses, same stop decisions whether every 10th iteration's loss comes out of the next W update's
+    contraction or out of a pass of its own; a stop right after a prefetch leaves the factors of that iteration."""
+    from torchnmf_b200 import engine as _engine
+    V, W0, H0 = _inputs((2048, 1024), (1024, 64), (2048, 64))
+    a = NMF(W=W0, H=H0).cuda()
+    na = a.fit(V.cuda(), 1, float("-inf"), 35, precision="f16")
+    monkeypatch.delattr(_engine.CudaNmfEngine, "loss_prefetch_w")
+    b = NMF(W=W0, H=H0).cuda()
+    nb = b.fit(V.cuda(), 1, float("-inf"), 35, precision="f16")
+    monkeypatch.undo()
+    assert na == nb == 35
+    assert torch.equal(a.W.data, b.W.data) and torch.equal(a.H.data, b.H.data)
+    c = NMF(W=W0, H=H0).cuda()
+    nc = c.fit(V.cuda(), 1, 1e9, 35, precision="f16")          # the stop rule fires at the first evaluation (iteration 10)
+    d = NMF(W=W0, H=H0).cuda()
+    nd = d.fit(V.cuda(), 1, float("-inf"), 10, precision="f16")
+    assert nc == nd == 10
+    assert torch.equal(c.W.data, d.W.data) and torch.equal(c.H.data, d.H.data)

@@ -211,3 +211,33 @@ def test_convolutive_models_refuse_sparse_targets_like_the_reference():
     V = torch.rand(1, 2, 6, 7).to_sparse()
     with pytest.raises(NotImplementedError):
         NMF2D(V.shape, 2, 2).fit(V)
+
+
+def test_fit_asks_for_the_prefetched_loss_only_when_a_w_update_follows():
+    """Host logic of the folded loss (nmfb200_nmf_loss_prefetch_w): every 10th iteration's loss may come out of the next W
+    update's pass -- but not the last evaluation of a fit, and not when W is frozen."""
+    calls = []
+
+    class Eng(OracleNmfEngine):
+        def loss(self, beta):
+            calls.append("loss")
+            return super().loss(beta)
+
+        def loss_prefetch_w(self, beta):
+            calls.append("prefetch")
+            return OracleNmfEngine.loss(self, beta)
+
+    torch.manual_seed(0)
+    V = torch.rand(20, 15)
+    m = NMF(W=torch.rand(15, 3), H=torch.rand(20, 3))
+    m._engine_factory = Eng
+    assert m.fit(V, 1, float("-inf"), 30) == 30
+    assert calls == ["loss", "prefetch", "prefetch", "loss"]          # init, @9, @19, @29 (nothing follows)
+    calls.clear()
+    m.fit(V, 1, float("-inf"), 25)
+    assert calls == ["loss", "prefetch", "prefetch"]
+    calls.clear()
+    f = NMF(W=torch.rand(15, 3), H=torch.rand(20, 3), trainable_W=False)
+    f._engine_factory = Eng
+    f.fit(V, 1, float("-inf"), 20)
+    assert calls == ["loss", "loss", "loss"]
