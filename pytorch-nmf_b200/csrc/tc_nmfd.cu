@@ -608,37 +608,141 @@ absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
+// colsum[r] = sum over `outer` slabs of `inner` consecutive partials each: part[(o R + r) inner + i]; block r, fixed order.
+// The block that finishes LAST also publishes kappa = sum(V) / sum_r colsum_W[r] colsum_H[r] (= sum of the reconstruction,
+// nmf.py:776-779) and the exponent of the ratio tile (kappa 2^p in [2^-4, 2^-3)) when no other refresh follows in this call:
+// two launches per refresh (prep, fold) instead of three.
+struct FoldTail {
+  const float* part;        // [(o R + r) inner + i]
+  float* colsum;            // [R] of the factor being refreshed
+  int outer, R, inner;
+  unsigned int* ticket;     // zero between launches
+  int do_kappa;
+  const double* vsum;
+  const float* colsum_all;  // [2 R]: W then H
+  float* kappa;
+  int* exps;
+};
+
+__global__ void __launch_bounds__(256)
+fold_colsum_kernel(const FoldTail f) {
+  __shared__ float sh[256];
+  __shared__ bool is_last;
+  const int r = blockIdx.x;
+  const int64_t n = (int64_t)f.outer * f.inner;
+  float a = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const int64_t o = i / f.inner, k = i - o * f.inner;
+    a += f.part[(o * f.R + r) * f.inner + k];
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    f.colsum[r] = sh[0];
+    __threadfence();                                            // this component's sum is visible before the ticket is
+    is_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  *f.ticket = 0u;
+  if (f.do_kappa) {
+    double dot = 0.0;
+    for (int q = 0; q < f.R; ++q) dot += (double)__ldcg(f.colsum_all + q) * (double)__ldcg(f.colsum_all + f.R + q);
+    const float k = (float)(*f.vsum / dot);
+    int e = 0;
+    const bool ok = k > 0.f && isfinite(k);
+    if (ok) { frexpf(k, &e); e = -3 - e; }
+    *f.kappa = ok ? k : 0.f;
+    f.exps[2] = e;
+  }
+}
+
 // One pass over W (C, R, T), block c: every fp16 operand copy of this row, scaled by 2^eW (eW from the max of W), written
 // 16 bytes per thread and step, plus the row's per-component sums (-> colsum_W, nmf.py:128-131):
 //   Wr16[c][r Tp + tt]           = W[c, r, Tp - 1 - tt]        (recon: shifts reversed so that the H window ascends)
 //   Wf16[c][r Tp + tt]           = W[c, r, tt]                 (dgrad, Toeplitz-tile formulation)
 //   Ws16[(c, grp, r%16, s)][u]   = W[c, r, u - s]              (dgrad, eight shifted copies)
 //   Wsh16[(c, s)][r Tq + u]      = W[c, r, s + A8 - u]         (recon, eight shifted copies)
-__global__ void __launch_bounds__(256)
+//
+// The eight shifted copies dominate (cfg3: 100 MB per refresh).  Every 16-byte store gathers eight CONSECUTIVE shifts of one
+// component, so the lanes of a warp read W at addresses eight floats apart: from a dense shared-memory row that is an 8-way
+// bank conflict per load, and with per-element index arithmetic and bounds checks the kernel was instruction-bound on top
+// (36 us at cfg3, 2.8 TB/s).  Hence the row is staged scaled and DE-INTERLEAVED by shift residue:
+//     stage[r][t & 7][(t >> 3) + F]   for t in [-8 F, 8 (S - F)),  zero outside [0, T)
+// (S slots per residue class, F leading ones).  For a fixed copy index s (an unrolled loop) element k of a store then
+// sits at a compile-time class and a compile-time slot offset from the thread's base, consecutive lanes read consecutive
+// words, and out-of-range shifts read the zero margins: eight loads with immediate offsets, four packs, one store.  Stores
+// whose eight shifts all fall outside [0, T) are skipped: those bytes are zero from tc_nmfd_create on and nobody writes them.
+__device__ __forceinline__ void prep_w_shifted(const float* __restrict__ stage, int S, int F, int R, int T, int Tq, int A8,
+                                               int ngroups, int c, __half* __restrict__ Ws16, __half* __restrict__ Wsh16) {
+  const int NV = Tq >> 3;                                  // 16-byte stores per row of either copy
+  const unsigned int magic = 0xFFFFFFFFu / (unsigned)NV + 1u;     // j / NV == umulhi(j, magic) for the j below (< 2^16)
+  const int64_t rows = (int64_t)ngroups * 128;
+  auto pack8 = [](const float (&v)[8]) {
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    return *reinterpret_cast<const uint4*>(h);
+  };
+  // one item = one (component r, 8-shift group vec): its eight stores (the eight copies of one layout) share every address
+  // computation; inside, copy index and element index are compile-time, so a load is [base + class S + immediate].
+  // dgrad copies: Ws16[(c, grp, r % 16, SH)][u + k] = W[c, r, u + k - SH]
+  for (int j = threadIdx.x; j < R * NV; j += 256) {
+    const int r = (int)__umulhi((unsigned)j, magic), vec = j - r * NV, u = vec << 3;
+    const float* up = stage + (int64_t)r * 8 * S + F + vec;                     // ascending windows
+    __half* ws = Ws16 + ((int64_t)c * rows + (int64_t)(r >> 4) * 128 + (r & 15) * 8) * Tq + u;       // + SH Tq
+#pragma unroll
+    for (int SH = 0; SH < 8; ++SH) {
+      if (u + 7 - SH >= 0 && u - SH < T) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = up[((k - SH) & 7) * S + ((k - SH) >> 3)];
+        *reinterpret_cast<uint4*>(ws + SH * Tq) = pack8(v);
+      }
+    }
+  }
+  // recon copies: Wsh16[(c, SH)][r Tq + u + k] = W[c, r, SH + A8 - u - k]
+  const int64_t wsh_step = (int64_t)R * Tq;
+  for (int j = threadIdx.x; j < R * NV; j += 256) {
+    const int r = (int)__umulhi((unsigned)j, magic), vec = j - r * NV, u = vec << 3;
+    const float* dn = stage + (int64_t)r * 8 * S + F + (A8 >> 3) - vec;         // descending windows
+    __half* wsh = Wsh16 + (int64_t)c * 8 * wsh_step + (int64_t)r * Tq + u;      // + SH R Tq
+#pragma unroll
+    for (int SH = 0; SH < 8; ++SH) {
+      if (SH + A8 - u >= 0 && SH + A8 - u - 7 < T) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = dn[((SH - k) & 7) * S + ((SH - k) >> 3)];
+        *reinterpret_cast<uint4*>(wsh + SH * wsh_step) = pack8(v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 8)     // 8 blocks per SM: the 1025 blocks of cfg3 run as one wave
 prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, int ngroups,
               const unsigned int* __restrict__ absmax, int* __restrict__ exps, __half* __restrict__ Wr16,
               __half* __restrict__ Wf16, __half* __restrict__ Ws16, __half* __restrict__ Wsh16, int A8,
-              float* __restrict__ cs_part, int use_smem) {
+              float* __restrict__ cs_part, int use_smem, int S, int F) {
   const int e = pow2_exp14(__uint_as_float(*absmax));
   if (blockIdx.x == 0 && threadIdx.x == 0) exps[0] = e;
   const float sc = exp2f((float)e);
   const int c = blockIdx.x;
   const float* Wg = W + (int64_t)c * R * T;
-  // this row of W (R x T fp32) is read ~20 times below: stage it in shared memory when it fits (dynamic: R T floats)
-  extern __shared__ float wrow[];
-  const float* Wc = Wg;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < R * T; i += 256) wrow[i] = Wg[i];
-    __syncthreads();
-    Wc = wrow;
-  }
-  auto w_at = [&](int r, int t) { return (r < R && t >= 0 && t < T) ? Wc[r * T + t] * sc : 0.f; };
+  extern __shared__ float stage[];
+  auto w_at = [&](int r, int t) { return (r < R && t >= 0 && t < T) ? Wg[r * T + t] * sc : 0.f; };
   auto pack8 = [&](const float (&v)[8]) {
     __half2 h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     return *reinterpret_cast<const uint4*>(h);
   };
+  // plain forward / reversed copies: only read by the Toeplitz-tile kernels (A/B switches, very long shifts)
   const int64_t rowlen = (int64_t)R * Tp;
   for (int i8 = threadIdx.x; Wr16 != nullptr && i8 < R * Tp / 8; i8 += 256) {
     const int i = i8 * 8, r = i / Tp, tt = i - r * Tp;
@@ -648,28 +752,51 @@ prep_w_kernel(const float* __restrict__ W, int C, int R, int T, int Tp, int Tq, 
     *reinterpret_cast<uint4*>(Wf16 + c * rowlen + i) = pack8(f);
     *reinterpret_cast<uint4*>(Wr16 + c * rowlen + i) = pack8(rv);
   }
-  const int64_t rows = (int64_t)ngroups * 128;
-  for (int i8 = threadIdx.x; i8 < rows * Tq / 8; i8 += 256) {
-    const int i = i8 * 8, n = i / Tq, u = i - n * Tq;
-    const int r = (n >> 7) * 16 + ((n & 127) >> 3), sh = n & 7;
-    float v[8];
+  if (use_smem) {
+    for (int i = threadIdx.x; i < R * 8 * S; i += 256) stage[i] = 0.f;
+    __syncthreads();
+    // the row's R T values: eight independent loads in flight per thread before the first dependent shared-memory store
+    // (a loop of load -> store pairs paid the full memory latency R times per block and was what bounded this kernel)
+    const int RT = R * T;
+    const unsigned int magic_t = 0xFFFFFFFFu / (unsigned)T + 1u;          // i / T == umulhi(i, magic_t): R T < 2^16 here
+    for (int i0 = threadIdx.x; i0 < RT; i0 += 256 * 8) {
+      float x[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = w_at(r, u + k - sh);
-    *reinterpret_cast<uint4*>(Ws16 + ((int64_t)c * rows + n) * Tq + u) = pack8(v);
-  }
-  // recon, eight-phase formulation: Wsh16[(c, s)][r Tq + u] = W[c, r, s + A8 - u]
-  for (int i8 = threadIdx.x; i8 < 8 * R * Tq / 8; i8 += 256) {
-    const int i = i8 * 8, sh = i / (R * Tq), ru = i - sh * (R * Tq), r = ru / Tq, u = ru - r * Tq;
-    float v[8];
+      for (int m = 0; m < 8; ++m) { const int i = i0 + m * 256; x[m] = i < RT ? Wg[i] : 0.f; }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = w_at(r, sh + A8 - u - k);
-    *reinterpret_cast<uint4*>(Wsh16 + ((int64_t)c * 8 + sh) * ((int64_t)R * Tq) + ru) = pack8(v);
+      for (int m = 0; m < 8; ++m) {
+        const int i = i0 + m * 256;
+        if (i < RT) {
+          const int r = (int)__umulhi((unsigned)i, magic_t), t = i - r * T;
+          stage[(r * 8 + (t & 7)) * S + (t >> 3) + F] = x[m] * sc;
+        }
+      }
+    }
+    __syncthreads();
+    prep_w_shifted(stage, S, F, R, T, Tq, A8, ngroups, c, Ws16, Wsh16);
+  } else {                           // a row of W too long to stage: straight from global memory, every store written
+    const int64_t rows = (int64_t)ngroups * 128;
+    for (int i8 = threadIdx.x; i8 < rows * Tq / 8; i8 += 256) {
+      const int i = i8 * 8, n = i / Tq, u = i - n * Tq;
+      const int r = (n >> 7) * 16 + ((n & 127) >> 3), sh = n & 7;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = w_at(r, u + k - sh);
+      *reinterpret_cast<uint4*>(Ws16 + ((int64_t)c * rows + n) * Tq + u) = pack8(v);
+    }
+    for (int i8 = threadIdx.x; i8 < 8 * R * Tq / 8; i8 += 256) {
+      const int i = i8 * 8, sh = i / (R * Tq), ru = i - sh * (R * Tq), r = ru / Tq, u = ru - r * Tq;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = w_at(r, sh + A8 - u - k);
+      *reinterpret_cast<uint4*>(Wsh16 + ((int64_t)c * 8 + sh) * ((int64_t)R * Tq) + ru) = pack8(v);
+    }
   }
   // per-component sums of this row: warp w takes r = w, w + 8, ...; fixed order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < R; r += 8) {
     float a = 0.f;
-    for (int t = lane; t < T; t += 32) a += Wc[r * T + t];
+    for (int t = lane; t < T; t += 32) a += Wg[r * T + t];
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) cs_part[(int64_t)c * R + r] = a;
   }
@@ -704,41 +831,6 @@ prep_h_kernel(const float* __restrict__ H, int Lin, int Lp, int padl, const unsi
     for (int i = 0; i < 8; ++i) t += sh[i];
     cs_part[row * gridDim.x + blockIdx.x] = t;
   }
-}
-
-// colsum[r] = sum over `outer` slabs of `inner` consecutive partials each: part[(o R + r) inner + i]; block r, fixed order
-__global__ void __launch_bounds__(256)
-fold_colsum_kernel(const float* __restrict__ part, int outer, int R, int inner, float* __restrict__ colsum) {
-  __shared__ float sh[256];
-  const int r = blockIdx.x;
-  const int64_t n = (int64_t)outer * inner;
-  float a = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += 256) {
-    const int64_t o = i / inner, k = i - o * inner;
-    a += part[(o * R + r) * inner + k];
-  }
-  sh[threadIdx.x] = a;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) colsum[r] = sh[0];
-}
-
-// kappa = sum(V) / sum_r colsum_W[r] colsum_H[r] (= sum of the reconstruction, nmf.py:776-779) and the exponent of the ratio
-// tile: kappa 2^p in [2^-4, 2^-3)
-__global__ void kappa_kernel(const double* __restrict__ vsum, const float* __restrict__ colsum, int R, float* __restrict__ kappa,
-                             int* __restrict__ exps) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double dot = 0.0;
-  for (int r = 0; r < R; ++r) dot += (double)colsum[r] * (double)colsum[R + r];
-  const float k = (float)(*vsum / dot);
-  int e = 0;
-  const bool ok = k > 0.f && isfinite(k);
-  if (ok) { frexpf(k, &e); e = -3 - e; }
-  *kappa = ok ? k : 0.f;
-  exps[2] = e;
 }
 
 __global__ void __launch_bounds__(256)
@@ -866,7 +958,8 @@ int tc_nmfd_create(TcNmfdState** out, const NmfdShape& d) {
     const int64_t np = std::max<int64_t>((int64_t)d.C * d.R, (int64_t)d.B * d.R * ceil_div(d.Lin, 2048));
     if (e == cudaSuccess) e = cudaMalloc(&s->cs_part, (size_t)np * sizeof(float));
   }
-  if (e == cudaSuccess) e = cudaMalloc(&s->exps, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&s->exps, 8 * sizeof(int));          // [0..3] exponents, [4..5] fold tickets
+  if (e == cudaSuccess) e = cudaMemset(s->exps, 0, 8 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&s->kappa, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&s->vsum, 257 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->loss_part, (size_t)s->loss_blocks * sizeof(double));
@@ -936,10 +1029,19 @@ NmfdTcParams base_params(TcNmfdState* s, const float* V) {
   return p;
 }
 
+// arguments of the fold launch after a preparation launch: fold `outer x R x inner` partial sums into colsum[which], then kappa if this is the
+// last refresh of the call
+FoldTail fold_tail_args(TcNmfdState* s, int which, int outer, int inner, int do_kappa) {
+  FoldTail f{};
+  f.part = s->cs_part; f.colsum = s->colsum + (which ? s->d.R : 0); f.outer = outer; f.R = s->d.R; f.inner = inner;
+  f.ticket = reinterpret_cast<unsigned int*>(s->exps + 4 + which); f.do_kappa = do_kappa;
+  f.vsum = s->vsum; f.colsum_all = s->colsum; f.kappa = s->kappa; f.exps = s->exps;
+  return f;
+}
+
 // bring the fp16 operand copies, column sums (and with them kappa) up to date with the fp32 factors: only what changed
 int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
   const NmfdShape& d = s->d;
-  const bool any = !s->w_fresh || !s->h_fresh;
   if (!s->w_fresh) {
     if (!s->aw_valid) {
       NMF_CUDA_CHECK(cudaMemsetAsync(s->absmax, 0, sizeof(unsigned int), st));
@@ -950,8 +1052,10 @@ int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
     // the reversed / forward copies are only read by the Toeplitz-tile kernels (A/B switches, or shifts too long for the
     // eight-phase kernels' shared-memory stages)
     const bool tile_copies = s->need_tile_copies;
-    const size_t wrow_bytes = (size_t)d.R * d.T * sizeof(float);
-    const int use_smem = wrow_bytes <= 200 * 1024 ? 1 : 0;
+    // staging layout of prep_w_kernel: S slots per shift-residue class, F of them leading zeros (shifts down to A8 + 1 - Tq)
+    const int F = (s->Tq - s->A8) / 8 + 2, S = s->Tq / 8 + F;
+    const size_t wrow_bytes = (size_t)d.R * 8 * S * sizeof(float);
+    const int use_smem = (wrow_bytes <= 200 * 1024 && (int64_t)d.R * d.T < 65536) ? 1 : 0;
     static size_t attr_bytes = 0;
     if (use_smem && wrow_bytes > 48 * 1024 && wrow_bytes > attr_bytes) {
       NMF_CUDA_CHECK(cudaFuncSetAttribute(prep_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wrow_bytes));
@@ -959,9 +1063,9 @@ int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
     }
     prep_w_kernel<<<d.C, 256, use_smem ? wrow_bytes : 0, st>>>(W, d.C, d.R, d.T, s->Tp, s->Tq, s->ngroups, s->absmax, s->exps,
                                                                tile_copies ? s->Wr16 : nullptr, s->Wf16, s->Ws16, s->Wsh16,
-                                                               s->A8, s->cs_part, use_smem);
+                                                               s->A8, s->cs_part, use_smem, S, F);
     NMF_LAUNCH_CHECK();
-    fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.C, d.R, 1, s->colsum);
+    fold_colsum_kernel<<<d.R, 256, 0, st>>>(fold_tail_args(s, 0, d.C, 1, /*do_kappa=*/s->h_fresh));
     NMF_LAUNCH_CHECK();
     s->w_fresh = true;
   }
@@ -976,13 +1080,9 @@ int refresh(TcNmfdState* s, const float* W, const float* H, cudaStream_t st) {
     dim3 gh((unsigned)nch, (unsigned)(d.B * d.R));
     prep_h_kernel<<<gh, 256, 0, st>>>(H, d.Lin, s->Lp, s->padl, s->absmax + 1, s->exps, s->Hp16, s->cs_part);
     NMF_LAUNCH_CHECK();
-    fold_colsum_kernel<<<d.R, 256, 0, st>>>(s->cs_part, d.B, d.R, nch, s->colsum + d.R);
+    fold_colsum_kernel<<<d.R, 256, 0, st>>>(fold_tail_args(s, 1, d.B, nch, /*do_kappa=*/1));
     NMF_LAUNCH_CHECK();
     s->h_fresh = true;
-  }
-  if (any) {
-    kappa_kernel<<<1, 32, 0, st>>>(s->vsum, s->colsum, d.R, s->kappa, s->exps);
-    NMF_LAUNCH_CHECK();
   }
   return 0;
 }

@@ -167,9 +167,69 @@ __global__ void minmax_stage2(const float* __restrict__ scratch, int nb, float* 
 
 }  // namespace
 
+// Four consecutive elements per thread (same row, same component: inner % 4 == 0), 16-byte loads of the parameter and of every
+// partial slab.  Same arithmetic per element as apply_update_kernel.
+__global__ void __launch_bounds__(256)
+apply_update_vec4_kernel(ApplyArgs a) {
+  const int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  float m = 0.f;
+  if (idx < a.numel) {
+    const int64_t row = idx / a.rowlen;
+    const int64_t off = row * a.ldp + (idx - row * a.rowlen);
+    const int r = (int)((idx / a.inner) % a.R);
+    const float sc = a.out_scale ? *a.out_scale : 1.0f;
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ch = 0; ch < a.nchunks; ++ch) {
+      const float4 t = *reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + off);
+      num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
+    }
+    float4 den = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.den) {
+      for (int ch = 0; ch < a.nchunks; ++ch) {
+        const float4 t = *reinterpret_cast<const float4*>(a.den + ch * a.chunk_stride + off);
+        den.x += t.x; den.y += t.y; den.z += t.z; den.w += t.w;
+      }
+    }
+    const float klden = a.den ? 0.f : a.kl_den[r];
+    float4 p = *reinterpret_cast<const float4*>(a.param + idx);
+    auto one = [&](float pv, float n, float d) {
+      n *= sc;
+      if (a.kappa) n = fmaf(*a.kappa, a.kappa_vec[r], n);
+      const float neg = fmaxf(n, 0.f) + kEps;                  // nmf.py:78
+      float pos = a.den ? fmaxf(d * sc, 0.f) + kEps : klden;   // nmf.py:83 / :368-369
+      if (a.l1 > 0.f) pos += a.l1;                             // nmf.py:85-86
+      if (a.l2 > 0.f) pos = fmaf(a.l2, pv, pos);               // nmf.py:87-88
+      float mult = neg / pos;                                  // nmf.py:89
+      if (a.gamma != 1.0f) mult = powf(mult, a.gamma);         // nmf.py:90-91
+      return pv * mult;                                        // nmf.py:92
+    };
+    p.x = one(p.x, num.x, den.x); p.y = one(p.y, num.y, den.y); p.z = one(p.z, num.z, den.z); p.w = one(p.w, num.w, den.w);
+    *reinterpret_cast<float4*>(a.param + idx) = p;
+    m = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
+  }
+  if (a.absmax_bits) {
+    __shared__ float wmax[8];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
+      if (m > 0.f) atomicMax(a.absmax_bits, __float_as_uint(m));
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 int apply_update(const ApplyArgs& a, cudaStream_t st) {
   if (a.numel <= 0) return 0;
-  apply_update_kernel<<<(unsigned)ceil_div(a.numel, 256), 256, 0, st>>>(a);
+  const bool vec4 = a.inner % 4 == 0 && a.rowlen % 4 == 0 && a.ldp % 4 == 0 && a.numel % 4 == 0 &&
+                    (a.nchunks == 1 || a.chunk_stride % 4 == 0) && aligned16(a.param) && aligned16(a.num) &&
+                    (!a.den || aligned16(a.den));
+  if (vec4)
+    apply_update_vec4_kernel<<<(unsigned)ceil_div(a.numel / 4, 256), 256, 0, st>>>(a);
+  else
+    apply_update_kernel<<<(unsigned)ceil_div(a.numel, 256), 256, 0, st>>>(a);
   NMF_LAUNCH_CHECK();
   return 0;
 }
