@@ -94,7 +94,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
     if (*reinterpret_cast<volatile unsigned int*>(&g_wait_abort[0]) != 0u) return;
     const long long now = clock64();
     if (t0 == 0) { t0 = now; continue; }
-    if (now - t0 > 2000000000LL) {
+    if (now - t0 > 20000000000LL) {      // ~10 s of SM clocks: far beyond any time-slice or profiler replay
       if (atomicCAS(&g_wait_abort[0], 0u, 1u) == 0u) {
         g_wait_abort[1] = blockIdx.x; g_wait_abort[2] = threadIdx.x; g_wait_abort[3] = bar; g_wait_abort[4] = parity;
         __threadfence();
