@@ -1085,87 +1085,211 @@ tc_apply_vec4_kernel(TcApplyArgs a) {
 // beta 2 denominators.  gram_part_kernel: per-slab partial G^T G (R x R, fp32); gram_sum_kernel folds the slabs in
 // fixed order.  tc_apply_eu_kernel: den_raw = F (G^T G) row by row (the reference's relu(S^T G), nmf.py:63,82, since
 // S = F G^T), num = O + den_raw with O = (V - S)-contraction from the tensor cores, then nmf.py:78-92.
+//
+// Both are small dense products (cfg5: 2.7e8 FMA each) and both were one-output-per-thread loops with two shared-memory
+// loads per FMA: ~100 us each at 65536 x 64, more than the tensor-core contraction they accompany (beta 2 ran at 570 us per
+// iteration with 211 us of contractions).  They are register-tiled now: a thread owns a TR x TR (Gram) or 4 x TR (ratio
+// stage) block of outputs, TR = Rp / 16, so that one 16-byte and a few broadcast loads feed 16 to 64 FMAs.
+template <int TR>
 __global__ void __launch_bounds__(256)
 gram_part_kernel(const float* __restrict__ x, int64_t rows, int R, int64_t rows_per_block, float* __restrict__ part) {
-  extern __shared__ float xs[];                 // [32][R]
+  constexpr int RP = 16 * TR;
+  __shared__ __align__(16) float xs[32][RP];    // a slab of 32 rows, zero-padded to RP columns
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
-  const int nout = R * R;
-  float acc[64];                                // up to 128*128/256 outputs per thread
+  float acc[TR][TR];
 #pragma unroll
-  for (int k = 0; k < 64; ++k) acc[k] = 0.f;
-  for (int64_t base = r0; base < r1; base += 32) {
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TR; ++j) acc[i][j] = 0.f;
+  // a slab's 32 x RP values travel global -> registers -> shared memory; the loads of slab s + 1 are issued before slab s is
+  // multiplied (a load -> store loop paid the memory latency once per element and thread: 5 of the kernel's 28 us were math)
+  constexpr int PER = 32 * RP / 256;
+  float pre[PER];
+  auto fetch = [&](int64_t base) {
     const int nr = (int)min((int64_t)32, r1 - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nr * R; i += 256) xs[i] = x[base * R + i];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      const int i = threadIdx.x + m * 256, rr = i / RP, col = i - rr * RP;
+      pre[m] = (rr < nr && col < R) ? x[(base + rr) * R + col] : 0.f;
+    }
+  };
+  if (r0 < r1) fetch(r0);
+  for (int64_t base = r0; base < r1; base += 32) {
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 64; ++k) {
-      const int o = threadIdx.x + k * 256;
-      if (o < nout) {
-        const int i = o / R, j = o - i * R;
-        float t = acc[k];
-        for (int rr = 0; rr < nr; ++rr) t = fmaf(xs[rr * R + i], xs[rr * R + j], t);
-        acc[k] = t;
+    for (int m = 0; m < PER; ++m) {
+      const int i = threadIdx.x + m * 256;
+      xs[i / RP][i % RP] = pre[m];
+    }
+    __syncthreads();
+    if (base + 32 < r1) fetch(base + 32);
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {            // rows in order: the same summation order per output as a plain loop
+      float av[TR], bv[TR];
+#pragma unroll
+      for (int i = 0; i < TR; ++i) av[i] = xs[rr][ty * TR + i];
+#pragma unroll
+      for (int j = 0; j < TR; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&xs[rr][tx * TR + j]);
+        bv[j] = t.x; bv[j + 1] = t.y; bv[j + 2] = t.z; bv[j + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int j = 0; j < TR; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  const int nout = R * R;
+#pragma unroll
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TR; ++j) {
+      const int gi = ty * TR + i, gj = tx * TR + j;
+      if (gi < R && gj < R) part[(int64_t)blockIdx.x * nout + gi * R + gj] = acc[i][j];
+    }
+}
+// out[o] = sum over the nb slabs, fixed order: warp w of a block sums slabs w, w + 8, ... of 32 outputs, then the eight
+// slice sums are added in order (one thread per output walking all slabs serially took 20 us for 256 slabs)
+__global__ void __launch_bounds__(256)
+gram_sum_kernel(const float* __restrict__ part, int nb, int nout, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
+  float t = 0.f;
+  if (o < nout) {
+#pragma unroll 4
+    for (int b = sl; b < nb; b += 8) t += part[(int64_t)b * nout + o];
+  }
+  red[sl][lane] = t;
+  __syncthreads();
+  if (sl == 0 && o < nout) {
+    float u = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) u += red[k][lane];
+    out[o] = u;
+  }
+}
+
+// Row tiles of 64: thread (ty, tx) owns rows 4 ty .. 4 ty + 3 and components TR tx .. TR tx + TR - 1 of the tile.  The tile's
+// old values are staged before anything is overwritten (pitch RP + 1: the four rows of a thread and the two row groups of a
+// warp fall into different banks), the Gram matrix once per block.  Dynamic shared memory: gram RP x RP | tile 64 x (RP + 1).
+template <int TR>
+__global__ void __launch_bounds__(256, TR == 4 ? 3 : 1)
+tc_apply_eu_kernel(TcApplyArgs a, const float* __restrict__ gram) {
+  constexpr int RP = 16 * TR, FP = RP + 1;
+  extern __shared__ __align__(16) float eu_smem[];
+  float* gs = eu_smem;                           // [RP][RP], zero-padded
+  float* fs = eu_smem + RP * RP;                 // [64][FP]
+  __shared__ float red[16][RP];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
+  const int64_t row1 = min(a.rows, row0 + a.rpb);
+  const int R = a.R;
+  // staging: sixteen independent loads in flight per thread, then the stores (see gram_part_kernel)
+  for (int i0 = threadIdx.x; i0 < RP * RP; i0 += 256 * 16) {
+    float t[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int i = i0 + m * 256, k = i / RP, r = i - k * RP;
+      t[m] = (k < R && r < R) ? gram[k * R + r] : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) gs[i0 + m * 256] = t[m];
+  }
+  float cs[TR], mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < TR; ++j) cs[j] = 0.f;
+  const float kap = *a.kappa;
+  for (int64_t base = row0; base < row1; base += 64) {
+    __syncthreads();                             // gram staged / the previous tile's reads are done
+    for (int i0 = threadIdx.x; i0 < 64 * RP; i0 += 256 * 16) {
+      float t[16];
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int i = i0 + m * 256, rl = i / RP, k = i - rl * RP;
+        const int64_t row = base + rl;
+        t[m] = (row < row1 && k < R) ? a.param[row * R + k] : 0.f;
+      }
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int i = i0 + m * 256;
+        fs[(i / RP) * FP + (i % RP)] = t[m];
+      }
+    }
+    // this thread's partial numerators (chunk sums, 16-byte loads; the partial rows are Rp = RP floats wide): issued before
+    // the product below so that their latency hides behind it
+    float numv[4][TR];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TR; ++j) numv[i][j] = 0.f;
+    for (int ch = 0; ch < a.nchunks; ++ch) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = base + ty * 4 + i;
+        if (row < row1) {
+#pragma unroll
+          for (int j = 0; j < TR; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(a.num + ch * a.chunk_stride + row * a.Rp + tx * TR + j);
+            numv[i][j] += t.x; numv[i][j + 1] += t.y; numv[i][j + 2] += t.z; numv[i][j + 3] += t.w;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    float acc[4][TR];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TR; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < RP; ++k) {               // (F G^T G)[row, r] = S^T-contraction, nmf.py:82; k ascending
+      float fv[4], gv[TR];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fv[i] = fs[(ty * 4 + i) * FP + k];
+#pragma unroll
+      for (int j = 0; j < TR; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&gs[k * RP + tx * TR + j]);
+        gv[j] = t.x; gv[j + 1] = t.y; gv[j + 2] = t.z; gv[j + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TR; ++j) acc[i][j] = fmaf(fv[i], gv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t row = base + ty * 4 + i;
+      if (row >= row1) continue;
+#pragma unroll
+      for (int j = 0; j < TR; ++j) {
+        const int r = tx * TR + j;
+        if (r >= R) continue;
+        const float den = acc[i][j];
+        const float num = fmaf(kap, den, numv[i][j]);            // numerator = (V - kappa S) G + kappa S G
+        float v = fs[(ty * 4 + i) * FP + r];
+        const float neg = fmaxf(num, 0.f) + kEps;                // nmf.py:78
+        float pos = fmaxf(den, 0.f) + kEps;                      // nmf.py:83
+        if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
+        if (a.l2 > 0.f) pos = fmaf(a.l2, v, pos);                 // nmf.py:87-88
+        float mult = neg / pos;                                   // nmf.py:89
+        if (a.gamma != 1.0f) mult = powf(mult, a.gamma);          // nmf.py:90-91 (gamma == 1 for beta 2)
+        v *= mult;                                                // nmf.py:92
+        a.param[row * R + r] = v;
+        cs[j] += v;
+        mx = fmaxf(mx, v);
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 64; ++k) {
-    const int o = threadIdx.x + k * 256;
-    if (o < nout) part[(int64_t)blockIdx.x * nout + o] = acc[k];
-  }
-}
-__global__ void __launch_bounds__(256)
-gram_sum_kernel(const float* __restrict__ part, int nb, int nout, float* __restrict__ out) {
-  const int o = blockIdx.x * 256 + threadIdx.x;
-  if (o >= nout) return;
-  float t = 0.f;
-  for (int b = 0; b < nb; ++b) t += part[(int64_t)b * nout + o];
-  out[o] = t;
-}
-
-// one thread per (row, r); a block stages its rows' old values in shared memory before anything is overwritten
-__global__ void __launch_bounds__(256)
-tc_apply_eu_kernel(TcApplyArgs a, const float* __restrict__ gram) {
-  extern __shared__ float rowbuf[];             // [rows_per_pass][R]
-  __shared__ float sh[256];
-  const int rows_per_pass = 256 / a.R > 0 ? 256 / a.R : 1;
-  const int rl = threadIdx.x / a.R, r = threadIdx.x - rl * a.R;
-  const bool active = rl < rows_per_pass;
-  const int64_t row0 = (int64_t)blockIdx.x * a.rpb;
-  const int64_t row1 = min(a.rows, row0 + a.rpb);
-  float cs = 0.f, mx = 0.f;
-  const float kap = *a.kappa;
-  for (int64_t base = row0; base < row1; base += rows_per_pass) {
-    const int64_t row = base + rl;
-    const bool ok = active && row < row1;
-    __syncthreads();
-    float v = 0.f;
-    if (ok) { v = a.param[row * a.R + r]; rowbuf[rl * a.R + r] = v; }
-    __syncthreads();
-    if (ok) {
-      float den = 0.f;                                          // (F G^T G)[row, r] = S^T-contraction, nmf.py:82
-      for (int k = 0; k < a.R; ++k) den = fmaf(rowbuf[rl * a.R + k], gram[k * a.R + r], den);
-      float num = kap * den;                                    // numerator = (V - kappa S) G + kappa S G
-      for (int ch = 0; ch < a.nchunks; ++ch) num += a.num[ch * a.chunk_stride + row * a.Rp + r];
-      const float neg = fmaxf(num, 0.f) + kEps;                // nmf.py:78
-      float pos = fmaxf(den, 0.f) + kEps;                      // nmf.py:83
-      if (a.l1 > 0.f) pos += a.l1;                              // nmf.py:85-86
-      if (a.l2 > 0.f) pos = fmaf(a.l2, v, pos);                 // nmf.py:87-88
-      float mult = neg / pos;                                   // nmf.py:89
-      if (a.gamma != 1.0f) mult = powf(mult, a.gamma);          // nmf.py:90-91 (gamma == 1 for beta 2)
-      v *= mult;                                                // nmf.py:92
-      a.param[row * a.R + r] = v;
-      cs += v;
-      mx = fmaxf(mx, v);
-    }
-  }
-  sh[threadIdx.x] = cs;
   __syncthreads();
-  if (threadIdx.x < a.R) {
+#pragma unroll
+  for (int j = 0; j < TR; ++j) red[ty][tx * TR + j] = cs[j];
+  __syncthreads();
+  if (threadIdx.x < R) {
     float t = 0.f;
-    for (int k = 0; k < rows_per_pass; ++k) t += sh[k * a.R + threadIdx.x];
+    for (int k = 0; k < 16; ++k) t += red[k][threadIdx.x];
     a.cs_part[(int64_t)blockIdx.x * 128 + threadIdx.x] = t;
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1947,13 +2071,24 @@ int apply_and_finish(TcState* s, int which, float* param, bool apply, const Plan
     const int64_t orows = which == 0 ? s->N : s->C;
     int64_t rpbg = round_up(ceil_div(orows, 256), 32);
     const int nb = (int)ceil_div(orows, rpbg);
-    gram_part_kernel<<<nb, 256, 32 * R * sizeof(float), st>>>(other, orows, R, rpbg, s->gram_part);
+    if (s->Rp == 64) gram_part_kernel<4><<<nb, 256, 0, st>>>(other, orows, R, rpbg, s->gram_part);
+    else gram_part_kernel<8><<<nb, 256, 0, st>>>(other, orows, R, rpbg, s->gram_part);
     NMF_LAUNCH_CHECK();
-    gram_sum_kernel<<<(unsigned)ceil_div(nout, 256), 256, 0, st>>>(s->gram_part, nb, nout, s->gram);
+    gram_sum_kernel<<<(unsigned)ceil_div(nout, 32), 256, 0, st>>>(s->gram_part, nb, nout, s->gram);
     NMF_LAUNCH_CHECK();
     a.den = nullptr;
-    const int rows_per_pass = 256 / R > 0 ? 256 / R : 1;
-    tc_apply_eu_kernel<<<blocks, 256, rows_per_pass * R * sizeof(float), st>>>(a, s->gram);
+    const int RPk = s->Rp == 64 ? 64 : 128;
+    const int eu_smem = (RPk * RPk + 64 * (RPk + 1)) * (int)sizeof(float);
+    if (RPk == 64) {
+      tc_apply_eu_kernel<4><<<blocks, 256, eu_smem, st>>>(a, s->gram);
+    } else {
+      static unsigned long long eu_attr_mask = 0;                    // > 48 KB of dynamic shared memory: opt in once per device
+      if (!((eu_attr_mask >> (s->device & 63)) & 1ull)) {
+        NMF_CUDA_CHECK(cudaFuncSetAttribute(tc_apply_eu_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, eu_smem));
+        eu_attr_mask |= 1ull << (s->device & 63);
+      }
+      tc_apply_eu_kernel<8><<<blocks, 256, eu_smem, st>>>(a, s->gram);
+    }
   } else if ((s->R & 3) == 0) {
     tc_apply_vec4_kernel<<<blocks, 256, 0, st>>>(a);
   } else {
