@@ -130,6 +130,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """The timed region starts now: only samples that arrive from here on are reported (nvidia-smi takes ~0.1 s to come up,
+        so it is started one warm-up step early and a short timed region would otherwise end before its first line)."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -140,7 +145,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        window = "timed region"
+        if len(self.lines) <= first and self.lines:      # region shorter than one sampling period: the warm-up step before it
+            first, window = 0, "last warm-up step + timed region"
+        self.window = window
+        for ln in self.lines[first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -154,7 +164,7 @@ class ClockSampler:
         sm.sort()
         top = sm[len(sm) // 2:] if sm else []        # samples under load = upper half
         med = top[len(top) // 2] if top else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": self.window}
 
 
 def dist_setup(n_gpus):
@@ -494,12 +504,16 @@ def main():
         assert n == a.iters
 
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    # warm-up outside the sampler, then sample clocks during the timed steps only
-    for _ in range(a.warmup):
+    # warm-up, with the sampler brought up during its last step; only the samples of the timed steps are reported
+    for i in range(a.warmup):
+        if sampler and i == a.warmup - 1:
+            sampler.start()
         step_resident()
     torch.cuda.synchronize()
     if sampler:
-        sampler.start()
+        if a.warmup == 0:
+            sampler.start()
+        sampler.mark()
     l0 = _capi.launch_count()
     ms = timed_steps(step_resident, a.steps, 0, world)
     launches = _capi.launch_count() - l0
