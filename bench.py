@@ -130,6 +130,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout=0.5):
+        """Block (briefly) until nvidia-smi has delivered its first line."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
     def mark(self):
         """The timed region starts now: only samples that arrive from here on are reported (nvidia-smi takes ~0.1 s to come up,
         so it is started one warm-up step early and a short timed region would otherwise end before its first line)."""
@@ -513,6 +519,7 @@ def main():
     if sampler:
         if a.warmup == 0:
             sampler.start()
+        sampler.wait_ready()          # rank 0 only; the other ranks meet it at the barrier that opens the timed region
         sampler.mark()
     l0 = _capi.launch_count()
     ms = timed_steps(step_resident, a.steps, 0, world)
