@@ -1,15 +1,16 @@
-"""Small helpers of the reference's `torchnmf/utils.py` (:5-13), same names and semantics."""
+"""The two helpers of the reference's `torchnmf/utils.py` (:5-13), same names, arguments and results."""
 import torch
 
 __all__ = ["normalize", "renorm_"]
 
 
-def normalize(x: torch.Tensor, axis=0) -> torch.Tensor:
-    """x scaled to unit sum along `axis` (utils.py:5-6)."""
-    return x / x.sum(axis, keepdim=True)
+def normalize(x, axis=0):
+    """`x` scaled so that it sums to one along `axis`."""
+    total = torch.sum(x, dim=axis, keepdim=True)
+    return torch.div(x, total)
 
 
-def renorm_(input: torch.Tensor, dim=0):
-    """In place: divide by the sum of squares over every axis but `dim` (utils.py:9-13)."""
-    dims = [d for d in range(input.dim()) if d != dim]
-    input /= (input * input).sum(dims, keepdim=True)
+def renorm_(input, dim=0):
+    """In place: every slice along `dim` divided by its sum of squares (taken over all the other axes)."""
+    others = tuple(d for d in range(input.dim()) if d != dim)
+    input.div_(input.square().sum(others, keepdim=True))
