@@ -149,7 +149,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, watts = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         first = getattr(self, "first", 0)
         window = "timed region"
@@ -164,13 +164,20 @@ class ClockSampler:
                 sm.append(float(f[0])); smax = float(f[1])
             except ValueError:
                 continue
+            try:
+                watts.append(float(f[2]))
+            except ValueError:
+                pass
             for nm, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
         top = sm[len(sm) // 2:] if sm else []        # samples under load = upper half
         med = top[len(top) // 2] if top else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": self.window}
+        watts.sort()
+        wtop = watts[len(watts) // 2:] if watts else []     # board power under load (the cfg2 line sits at the cap)
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": self.window,
+                "board_power_w": wtop[len(wtop) // 2] if wtop else None}
 
 
 def dist_setup(n_gpus):
