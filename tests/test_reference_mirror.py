@@ -1,0 +1,65 @@
+"""The reference's own CPU tests that touch no fit kernel, run unchanged in spirit against this package:
+tests/test_metrics.py:6-19 (value ranges of beta_div / sparseness) and tests/test_trainer.py:10-53 (BetaMu on a composed
+nn.Sequential of three NMF layers, SparsityProj on one factor -- non-negativity after every step).  BetaMu takes its generic
+autograd path here (a composed graph is not a single leaf); SparsityProj's projection is the library's, so on this GPU-less
+side the oracle's restatement stands in for it (tests/test_hoyer.py pins both to the reference's outputs)."""
+import pytest
+import torch
+from torch import nn
+
+from oracle import hoyer_oracle as hoy
+from torchnmf_b200 import NMF, BetaMu, SparsityProj
+from torchnmf_b200 import trainer as _trainer
+from torchnmf_b200.metrics import beta_div, sparseness
+
+
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1, 1.5, 2, 3])
+@pytest.mark.parametrize("x, y", [(torch.zeros(100), torch.rand(100)), (torch.rand(100), torch.rand(100)),
+                                  (torch.rand(100), torch.zeros(100)), (torch.zeros(100), torch.zeros(100))])
+def test_beta_value_range(beta, x, y):
+    loss = beta_div(x, y, beta)
+    assert not torch.any(torch.isnan(loss)), loss.item()
+    assert not torch.any(loss < 0), loss.item()
+
+
+@pytest.mark.parametrize("x", [torch.rand(100)])
+def test_sparseness_value_range(x):
+    loss = sparseness(x)
+    assert not torch.any(torch.isnan(loss)), loss.item()
+    assert 0.0 <= float(loss) <= 1.0
+
+
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1, 1.5, 2, 3])
+@pytest.mark.parametrize("l1_reg, l2_reg, orthogonal", [(0, 0, 0), (1e-3, 0, 1e-2), (0, 1e-3, 0), (1e-3, 1e-3, 1e-2)])
+def test_beta_trainer(beta, l1_reg, l2_reg, orthogonal):
+    torch.manual_seed(0)
+    m = nn.Sequential(NMF((100, 16), rank=8), NMF(W=(32, 16)), NMF(W=(50, 32)))
+    target = torch.rand(100, 50)
+    trainer = BetaMu(m.parameters(), beta, l1_reg, l2_reg, orthogonal)
+
+    def closure():
+        trainer.zero_grad()
+        return target, m(None)
+
+    for _ in range(10):
+        trainer.step(closure)
+        assert set(trainer.last_step_paths) == {"autograd"}
+        for p in m.parameters():
+            assert torch.all(p >= 0.)
+
+
+@pytest.mark.parametrize("attr", ["W", "H"])
+def test_sparse_trainer(attr, monkeypatch):
+    monkeypatch.setattr(_trainer, "_project_slices_", lambda p, dim, k1, k2: p.copy_(hoy.project_slices(p, dim, k1, k2)))
+    torch.manual_seed(0)
+    m = NMF((100, 50))
+    target = torch.rand(100, 50)
+    trainer = SparsityProj([getattr(m, attr)], 0.2)
+
+    def closure():
+        trainer.zero_grad()
+        return beta_div(m(None), target)
+
+    for _ in range(10):
+        trainer.step(closure)
+        assert torch.all(getattr(m, attr) >= 0.)
