@@ -63,3 +63,21 @@ def test_sparse_trainer(attr, monkeypatch):
     for _ in range(10):
         trainer.step(closure)
         assert torch.all(getattr(m, attr) >= 0.)
+
+
+# tests/test_nmf.py:120-136 (`test_sparse_fit`): every beta branch, with and without a constraint, runs its max_iter iterations and
+# stays finite.  Host logic of `sparse_fit` with the oracle in place of the library (the GPU path: tests/test_hoyer.py).
+@pytest.mark.parametrize("beta", [-1, 0, 0.5, 1, 1.5, 2, 2.5])
+@pytest.mark.parametrize("sW, sH", [(None,) * 2, (0.3, None), (None, 0.3)])
+def test_sparse_fit(beta, sW, sH):
+    from oracle_engine import OracleNmfEngine
+    torch.manual_seed(0)
+    max_iter = 20
+    V = torch.rand(100, 50) + 1e-3
+    m = NMF(V.shape, 8)
+    m._engine_factory = OracleNmfEngine
+    n_iter = m.sparse_fit(V, beta, max_iter, beta == 2, sW, sH)
+    assert n_iter == max_iter
+    assert not torch.any(torch.isnan(m.W))
+    assert not torch.any(torch.isnan(m.H))
+    assert torch.all(m.W >= 0) and torch.all(m.H >= 0)
