@@ -459,6 +459,20 @@ def hoyer_cases():
     run_sfit("sfit_nmfd_kl_sH", ref_nmf.NMFD, (2, 21, 61), (21, 4, 5), (2, 4, 57), 1, 20, None, 0.4)
     run_sfit("sfit_nmf2d_both", ref_nmf.NMF2D, (1, 6, 20, 30), (6, 3, 3, 4), (1, 3, 18, 27), 2, 15, 0.5, 0.4)
 
+    # --- sparse_fit on a SPARSE target (the reference's SDDMM derivation, nmf.py:603-638): this repo densifies such a target,
+    # so the fixture pins "densified == the reference's sparse path" (its own tests/test_nmf_sparse.py:38-79 asserts the same
+    # about itself).  Named spv_*: CPU tests only.
+    for name, sW, sH in (("spv_sW", 0.3, None), ("spv_sH", None, 0.3)):
+        torch.manual_seed(5)
+        Vd = torch.rand(200, 150).bfloat16().float()
+        Vd = Vd * (Vd > 0.9)
+        torch.manual_seed(6)
+        W0 = torch.randn(150, 8).abs(); H0 = torch.randn(200, 8).abs()
+        m = ref_nmf.NMF(W=W0, H=H0)
+        n_iter = m.sparse_fit(Vd.to_sparse(), 2, 8, False, sW, sH)
+        put(name, dict(V=Vd, W0=W0, H0=H0, W=m.W, H=m.H),
+            dict(beta=2, iters=8, n_iter=n_iter, sW=-1 if sW is None else sW, sH=-1 if sH is None else sH))
+
     # --- trainer.SparsityProj (trainer.py:124-190): steps on one NMF module, closure = beta_div of its reconstruction ---
     # (short runs: once the loss flattens, `loss <= init_loss` is decided by rounding and the step sizes of two
     # implementations part ways)

@@ -210,7 +210,7 @@ class BaseComponent(torch.nn.Module):
                    else self._build_engine(Vd, Wd, Hd, precision))
         else:
             Wd, Hd = W.data, H.data
-            eng = self._engine_factory(V, Wd, Hd)
+            eng = self._engine_factory(V.to_dense() if (sparse_target and not sparse_kernels) else V, Wd, Hd)
         if group is not None:
             if eng.kind != "nmf":
                 raise NotImplementedError("row sharding is implemented for NMF only (NMFD: replicas only)")

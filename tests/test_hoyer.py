@@ -120,6 +120,21 @@ def test_sparse_fit_host_logic_matches_reference(name):
     assert _err(m.H.data, _t(c, "H"), *tol) <= 1.0
 
 
+@pytest.mark.parametrize("name", [n for n in NAMES if n.startswith("spv_")])
+def test_sparse_fit_on_a_sparse_target_is_the_references_sparse_path(name):
+    """The reference ran these through its sparse (SDDMM) derivation, nmf.py:603-638; here a sparse target of `sparse_fit` is
+    densified: the oracle on the dense matrix and the host logic on the COO tensor both land on the reference's factors."""
+    c = _case(name)
+    V = _t(c, "V")
+    W, H, n_iter, _ = hoy.sparse_fit(V, _t(c, "W0"), _t(c, "H0"), 2, int(c["iters"]), _opt(c, "sW"), _opt(c, "sH"))
+    assert n_iter == int(c["n_iter"])
+    assert _err(W, _t(c, "W"), *ORACLE_TOL) <= 1.0 and _err(H, _t(c, "H"), *ORACLE_TOL) <= 1.0
+    m = NMF(W=_t(c, "W0"), H=_t(c, "H0"))
+    m._engine_factory = OracleNmfEngine
+    m.sparse_fit(V.to_sparse(), 2, int(c["iters"]), False, _opt(c, "sW"), _opt(c, "sH"))
+    assert _err(m.W.data, _t(c, "W"), *ORACLE_TOL) <= 1.0 and _err(m.H.data, _t(c, "H"), *ORACLE_TOL) <= 1.0
+
+
 @pytest.mark.parametrize("name", SPROJ)
 def test_sparsity_proj_host_logic_matches_reference(name, monkeypatch):
     c = _case(name)
