@@ -81,3 +81,31 @@ def test_sparse_fit(beta, sW, sH):
     assert not torch.any(torch.isnan(m.W))
     assert not torch.any(torch.isnan(m.H))
     assert torch.all(m.W >= 0) and torch.all(m.H >= 0)
+
+
+def test_public_surface_covers_the_references():
+    """Every public name of torchnmf 0.3.5 (its `__all__` lists, the optimizers of trainer.py, the functions of metrics.py and
+    utils.py, the module-level helpers trainer.py imports from nmf.py) exists here under the same module path."""
+    import inspect
+    import torchnmf_b200 as pkg
+    want = {
+        "nmf": ["BaseComponent", "NMF", "NMFD", "NMF2D", "NMF3D", "_proj_func", "_get_norm", "_renorm"],       # nmf.py:16-18, :21, :134, :142
+        "plca": ["PLCA", "SIPLCA", "SIPLCA2", "SIPLCA3", "BaseComponent"],                                      # plca.py:13-15
+        "trainer": ["BetaMu", "SparsityProj"],                                                                   # trainer.py:7, :124
+        "metrics": ["kl_div", "euclidean", "is_div", "beta_div", "sparseness"],                                 # metrics.py:6-115
+        "utils": ["normalize", "renorm_"],                                                                       # utils.py:5-13
+        "constants": ["eps"],                                                                                    # constants.py:3
+    }
+    for mod, names in want.items():
+        m = getattr(pkg, mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
+    for cls, methods in ((pkg.nmf.BaseComponent, ["fit", "sparse_fit", "forward", "reconstruct", "extra_repr"]),
+                         (pkg.plca.BaseComponent, ["fit", "forward", "reconstruct"])):
+        for meth in methods:
+            assert callable(getattr(cls, meth)), f"{cls.__name__}.{meth}"
+    # positional signatures of the fit entry points are the reference's (nmf.py:298-306, :412-419; plca.py:193-201)
+    assert list(inspect.signature(pkg.NMF.fit).parameters)[:8] == ["self", "V", "beta", "tol", "max_iter", "verbose", "alpha", "l1_ratio"]
+    assert list(inspect.signature(pkg.NMF.sparse_fit).parameters)[:7] == ["self", "V", "beta", "max_iter", "verbose", "sW", "sH"]
+    assert list(inspect.signature(pkg.PLCA.fit).parameters)[:8] == ["self", "V", "tol", "max_iter", "verbose", "W_alpha", "H_alpha", "Z_alpha"]
+    assert float(pkg.constants.eps) == float(torch.finfo(torch.float32).eps)
